@@ -1,0 +1,435 @@
+// C-ABI entry points (include/s2s_b200.h) and the host-side pipeline that strings the kernels together.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "s2s_kernels.h"
+#include "s2s_tc.h"
+
+namespace s2s {
+
+static thread_local char g_err[512] = "";
+long long g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace s2s
+
+using namespace s2s;
+
+struct s2s_engine {
+  int device = 0;
+  int sm_count = 148;
+  s2s_config cfg{};
+  float* d_f32 = nullptr;   // derived fp32 weights
+  __half* d_f16 = nullptr;  // fp16 operand copies (tcgen05 path)
+  DevWeights dw{};
+  int64_t batch_chunks = 4096;
+  TcState tc{};
+};
+
+// ------------------------------------------------------------------------------------------------
+// derived weights
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Packer {
+  std::vector<float> f;
+  std::vector<__half> h;
+  int64_t put(const float* src, int64_t n) {  // returns offset (floats), 64-float aligned
+    int64_t off = (int64_t)f.size();
+    f.insert(f.end(), src, src + n);
+    while (f.size() % 64) f.push_back(0.f);
+    return off;
+  }
+  // transpose [rows][cols] -> [cols][rows]
+  int64_t put_t(const float* src, int rows, int cols) {
+    std::vector<float> t((size_t)rows * cols);
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < cols; ++c) t[(size_t)c * rows + r] = src[(size_t)r * cols + c];
+    return put(t.data(), (int64_t)rows * cols);
+  }
+  int64_t put_h(const float* src, int64_t n) {
+    int64_t off = (int64_t)h.size();
+    for (int64_t i = 0; i < n; ++i) h.push_back(__float2half_rn(src[i]));
+    while (h.size() % 64) h.push_back(__float2half_rn(0.f));
+    return off;
+  }
+};
+
+struct BlockOff {
+  int64_t wqkv_t, bqkv, fc_t, fc_b, w1_t, b1, w2_t, b2, ln1_w, ln1_b, ln2_w, ln2_b, wqkv_h, fc_h, w1_h, w2_h;
+};
+
+BlockOff pack_block(Packer& pk, const BlockW& b) {
+  BlockOff o{};
+  // concatenated [192][64] (q rows, then k, then v), transposed to [64][192]
+  std::vector<float> cat(192 * 64), bias(192);
+  memcpy(cat.data(), b.wq, 4096 * 4);
+  memcpy(cat.data() + 4096, b.wk, 4096 * 4);
+  memcpy(cat.data() + 8192, b.wv, 4096 * 4);
+  memcpy(bias.data(), b.bq, 64 * 4);
+  memcpy(bias.data() + 64, b.bk, 64 * 4);
+  memcpy(bias.data() + 128, b.bv, 64 * 4);
+  o.wqkv_t = pk.put_t(cat.data(), 192, 64);
+  o.bqkv = pk.put(bias.data(), 192);
+  o.fc_t = pk.put_t(b.fc_w, 64, 64);
+  o.fc_b = pk.put(b.fc_b, 64);
+  o.w1_t = pk.put_t(b.w1, 256, 64);
+  o.b1 = pk.put(b.b1, 256);
+  o.w2_t = pk.put_t(b.w2, 64, 256);
+  o.b2 = pk.put(b.b2, 64);
+  o.ln1_w = pk.put(b.ln1_w, 64);
+  o.ln1_b = pk.put(b.ln1_b, 64);
+  o.ln2_w = pk.put(b.ln2_w, 64);
+  o.ln2_b = pk.put(b.ln2_b, 64);
+  o.wqkv_h = pk.put_h(cat.data(), 192 * 64);
+  o.fc_h = pk.put_h(b.fc_w, 64 * 64);
+  o.w1_h = pk.put_h(b.w1, 256 * 64);
+  o.w2_h = pk.put_h(b.w2, 64 * 256);
+  return o;
+}
+
+void bind_block(BlockDev& d, const BlockOff& o, const float* f, const __half* h) {
+  d.wqkv_t = f + o.wqkv_t; d.bqkv = f + o.bqkv; d.fc_t = f + o.fc_t; d.fc_b = f + o.fc_b;
+  d.w1_t = f + o.w1_t; d.b1 = f + o.b1; d.w2_t = f + o.w2_t; d.b2 = f + o.b2;
+  d.ln1_w = f + o.ln1_w; d.ln1_b = f + o.ln1_b; d.ln2_w = f + o.ln2_w; d.ln2_b = f + o.ln2_b;
+  d.wqkv_h = h + o.wqkv_h; d.fc_h = h + o.fc_h; d.w1_h = h + o.w1_h; d.w2_h = h + o.w2_h;
+}
+
+int check_config(const s2s_config* c) {
+  if (!c) { set_error("null config"); return -1; }
+  if (c->dmodel != 64 || c->dff != 256 || c->heads != 8 || c->max_dna_len != 16 || c->max_signal_len != 250 ||
+      c->pre_layers != 1) {
+    set_error("unsupported architecture: dmodel=%d dff=%d heads=%d max_dna_len=%d max_signal_len=%d pre_layers=%d "
+              "(compiled for 64/256/8/16/250/1)", c->dmodel, c->dff, c->heads, c->max_dna_len, c->max_signal_len,
+              c->pre_layers);
+    return -1;
+  }
+  if (c->seq_kmer < 1 || c->seq_kmer > 12 || c->encoder_layers < 1 || c->encoder_layers > 4 ||
+      c->decoder_layers < 1 || c->decoder_layers > 4) {
+    set_error("unsupported seq_kmer=%d / encoder_layers=%d / decoder_layers=%d", c->seq_kmer, c->encoder_layers,
+              c->decoder_layers);
+    return -1;
+  }
+  return 0;
+}
+
+// ---- workspace carving ---------------------------------------------------------------------------
+struct Carver {
+  char* base;
+  int64_t off = 0;
+  explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+  template <typename T>
+  T* take(int64_t n) {
+    T* p = reinterpret_cast<T*>(base ? base + off : nullptr);
+    off += align_up(n * (int64_t)sizeof(T), 256);
+    return p;
+  }
+};
+
+struct Workspace {
+  // whole call
+  int32_t *chunk_read, *chunk_nk;
+  int64_t* chunk_base;
+  float* pa;
+  void* compact_ws;
+  int64_t compact_bytes;
+  // per sub-batch
+  float *emb, *xe, *qkv_e, *att_e, *ye, *he, *h3, *sigma;
+  int32_t *dur, *total;
+  float *xd, *qkv_d, *att_d, *yd, *hd, *sigma_ext;
+  TcBuffers tcb;
+};
+
+int64_t carve(Workspace& w, void* base, const s2s_engine* h, int64_t n_chunks, int64_t n_reads, bool need_pa) {
+  Carver cv(base);
+  const int64_t bc = n_chunks < h->batch_chunks ? n_chunks : h->batch_chunks;
+  const int64_t me = bc * S2S_L_ENC, md = bc * S2S_L_DEC_PAD;
+  w.chunk_read = cv.take<int32_t>(n_chunks);
+  w.chunk_nk = cv.take<int32_t>(n_chunks);
+  w.chunk_base = cv.take<int64_t>(n_chunks);
+  w.pa = need_pa ? cv.take<float>(n_chunks * S2S_L_DEC) : nullptr;
+  w.compact_bytes = compact_workspace_bytes(n_chunks);
+  w.compact_ws = cv.take<char>(w.compact_bytes);
+  w.emb = cv.take<float>(me * 64);
+  w.xe = cv.take<float>(me * 64);
+  w.qkv_e = cv.take<float>(me * 192);
+  w.att_e = cv.take<float>(me * 64);
+  w.ye = cv.take<float>(me * 64);
+  w.he = cv.take<float>(me * 256);
+  w.h3 = cv.take<float>(me * 192);
+  w.sigma = cv.take<float>(me);
+  w.dur = cv.take<int32_t>(me);
+  w.total = cv.take<int32_t>(bc);
+  w.xd = cv.take<float>(md * 64);
+  w.qkv_d = cv.take<float>(md * 192);
+  w.att_d = cv.take<float>(md * 64);
+  w.yd = cv.take<float>(md * 64);
+  w.hd = cv.take<float>(md * 256);
+  w.sigma_ext = cv.take<float>(bc * S2S_L_DEC);
+  tc_carve(w.tcb, cv.base, cv.off, bc);
+  (void)n_reads;
+  return cv.off;
+}
+
+int tap_copy(void* dst, const void* src, int64_t bytes, cudaStream_t st) {
+  if (dst && bytes > 0) S2S_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// One FFT block in fp32 on CUDA cores.  x (input and residual) -> x (output); y, qkv, att, hbuf scratch.
+int fft_block_f32(const BlockDev& b, float* x, float* y, float* qkv, float* att, float* hbuf, int64_t n_chunks, int L,
+                  int rows_per_chunk, cudaStream_t st) {
+  const int64_t M = n_chunks * rows_per_chunk;
+  if (launch_linear_f32(x, b.wqkv_t, b.bqkv, nullptr, nullptr, nullptr, qkv, M, 64, 192, EPI_BIAS, st)) return -1;
+  if (launch_attention_f32(qkv, att, n_chunks, L, rows_per_chunk, st)) return -1;
+  if (launch_linear_f32(att, b.fc_t, b.fc_b, x, b.ln1_w, b.ln1_b, y, M, 64, 64, EPI_BIAS_RES_LN, st)) return -1;
+  if (launch_linear_f32(y, b.w1_t, b.b1, nullptr, nullptr, nullptr, hbuf, M, 64, 256, EPI_BIAS_RELU, st)) return -1;
+  if (launch_linear_f32(hbuf, b.w2_t, b.b2, y, b.ln2_w, b.ln2_b, x, M, 256, 64, EPI_BIAS_RES_LN, st)) return -1;
+  return 0;
+}
+
+// The whole path for chunks [0, n_chunks): writes pA rows into pa_out[n_chunks*250].
+int run_pipeline(s2s_engine* h, const uint8_t* bases, const int8_t* codes, const Workspace& w, int64_t n_chunks,
+                 const s2s_run_opts& opts, float* pa_out, const s2s_taps* taps, cudaStream_t st) {
+  const DevWeights& dw = h->dw;
+  const int k = h->cfg.seq_kmer;
+  for (int64_t c0 = 0; c0 < n_chunks; c0 += h->batch_chunks) {
+    const int64_t bc = (n_chunks - c0) < h->batch_chunks ? (n_chunks - c0) : h->batch_chunks;
+    const int64_t me = bc * S2S_L_ENC;
+    s2s_run_opts o = opts;
+    o.chunk_id_base = opts.chunk_id_base + (uint64_t)c0;
+    // K-A
+    if (launch_embed(dw, bases, bases ? w.chunk_base + c0 : nullptr, bases ? w.chunk_nk + c0 : nullptr,
+                     codes ? codes + c0 * S2S_L_ENC * k : nullptr, bc, w.emb, w.xe, st)) return -1;
+    // encoder (modules.py:82-87)
+    for (int l = 0; l < h->cfg.encoder_layers; ++l)
+      if (fft_block_f32(dw.enc[l], w.xe, w.ye, w.qkv_e, w.att_e, w.he, bc, S2S_L_ENC, S2S_L_ENC, st)) return -1;
+    // samplers (K-C)
+    if (launch_linear_f32(w.emb, dw.smp0_t, dw.smp0_b, nullptr, nullptr, nullptr, w.h3, me, 64, 192, EPI_BIAS_RELU, st))
+      return -1;
+    if (launch_sampler_heads(dw, w.h3, me, o, w.sigma, w.dur, taps && taps->conc_dev ? taps->conc_dev + c0 * 16 : nullptr,
+                             taps && taps->rate_dev ? taps->rate_dev + c0 * 16 : nullptr,
+                             taps && taps->dur_float_dev ? taps->dur_float_dev + c0 * 16 : nullptr, st)) return -1;
+    // K-D
+    if (launch_length_regulate(w.xe, w.sigma, w.dur, bc, dw.dec_pos, w.xd, S2S_L_DEC_PAD, w.sigma_ext, w.total,
+                               taps && taps->lr_out_dev ? taps->lr_out_dev + c0 * S2S_L_DEC * 64 : nullptr, st)) return -1;
+    if (taps) {
+      if (tap_copy(taps->emb_out_dev ? taps->emb_out_dev + c0 * 16 * 64 : nullptr, w.emb, me * 64 * 4, st)) return -1;
+      if (tap_copy(taps->enc_out_dev ? taps->enc_out_dev + c0 * 16 * 64 : nullptr, w.xe, me * 64 * 4, st)) return -1;
+      if (tap_copy(taps->sigma_dev ? taps->sigma_dev + c0 * 16 : nullptr, w.sigma, me * 4, st)) return -1;
+      if (tap_copy(taps->dur_int_dev ? taps->dur_int_dev + c0 * 16 : nullptr, w.dur, me * 4, st)) return -1;
+      if (tap_copy(taps->sigma_ext_dev ? taps->sigma_ext_dev + c0 * S2S_L_DEC : nullptr, w.sigma_ext,
+                   bc * S2S_L_DEC * 4, st)) return -1;
+    }
+    // decoder (modules.py:138-139)
+    if (opts.precision == S2S_PREC_FP32) {
+      for (int l = 0; l < h->cfg.decoder_layers; ++l)
+        if (fft_block_f32(dw.dec[l], w.xd, w.yd, w.qkv_d, w.att_d, w.hd, bc, S2S_L_DEC, S2S_L_DEC_PAD, st)) return -1;
+    } else {
+      if (tc_decoder(h->tc, dw, w.tcb, w.xd, bc, st)) return -1;
+    }
+    // K-F
+    float* pa_b = pa_out + c0 * S2S_L_DEC;
+    if (launch_out_epilogue(dw, w.xd, w.sigma_ext, bc, o, taps && taps->p_dev ? taps->p_dev + c0 * S2S_L_DEC : nullptr,
+                            pa_b, st)) return -1;
+    if (taps && tap_copy(taps->pa_dev ? taps->pa_dev + c0 * S2S_L_DEC : nullptr, pa_b, bc * S2S_L_DEC * 4, st)) return -1;
+  }
+  return 0;
+}
+
+int check_opts(const s2s_run_opts* o) {
+  if (!o) { set_error("null run options"); return -1; }
+  if (o->duration_mode < 0 || o->duration_mode > 2 || o->noise_mode < 0 || o->noise_mode > 2 ||
+      (o->precision != S2S_PREC_FP16_TC && o->precision != S2S_PREC_FP32)) {
+    set_error("bad run options: duration_mode=%d noise_mode=%d precision=%d", o->duration_mode, o->noise_mode, o->precision);
+    return -1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// extern "C"
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* s2s_last_error(void) { return g_err; }
+int s2s_abi_version(void) { return S2S_ABI_VERSION; }
+int64_t s2s_launch_count(void) { return g_launch_count; }
+
+int64_t s2s_weights_count(const s2s_config* cfg) {
+  if (check_config(cfg)) return -1;
+  return weights_count(*cfg);
+}
+
+int64_t s2s_chunks_of_read(int64_t read_len, int32_t seq_kmer) {
+  int64_t n = read_len - seq_kmer + 1;
+  return n <= 0 ? 0 : (n + S2S_L_ENC - 1) / S2S_L_ENC;
+}
+
+int s2s_create(const float* weights_host, int64_t n_weights, const s2s_config* cfg, int device, s2s_handle* out) {
+  if (!out) { set_error("null out handle"); return -1; }
+  *out = nullptr;
+  if (check_config(cfg)) return -1;
+  if (!weights_host || n_weights != weights_count(*cfg)) {
+    set_error("weight blob has %lld floats, expected %lld", (long long)n_weights, (long long)weights_count(*cfg));
+    return -1;
+  }
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    set_error("no CUDA device available (%s): the s2s_b200 path has no CPU fallback", cudaGetErrorString(e));
+    return -2;
+  }
+  S2S_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  S2S_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return -2;
+  }
+  s2s_engine* h = new s2s_engine();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->cfg = *cfg;
+  if (const char* env = getenv("S2S_BATCH_CHUNKS")) {
+    long v = atol(env);
+    if (v >= 1) h->batch_chunks = v;
+  }
+  const Weights W = map_weights(weights_host, *cfg);
+  Packer pk;
+  const int k5 = 5 * cfg->seq_kmer;
+  int64_t o_enc_pos = pk.put(W.enc_pos, 16 * 64), o_dec_pos = pk.put(W.dec_pos, 250 * 64);
+  int64_t o_src_t = pk.put_t(W.src_w, 64, k5), o_src_b = pk.put(W.src_b, 64);
+  int64_t o_pre_t = pk.put_t(W.pre_w, 64, 64), o_pre_b = pk.put(W.pre_b, 64);
+  std::vector<float> s0(192 * 64), s0b(192), s3(3 * 64), s3b(3);
+  const MlpW* mlps[3] = {&W.conc, &W.rate, &W.noise};
+  for (int m = 0; m < 3; ++m) {
+    memcpy(s0.data() + m * 4096, mlps[m]->w0, 4096 * 4);
+    memcpy(s0b.data() + m * 64, mlps[m]->b0, 64 * 4);
+    memcpy(s3.data() + m * 64, mlps[m]->w3, 64 * 4);
+    s3b[m] = mlps[m]->b3[0];
+  }
+  int64_t o_s0t = pk.put_t(s0.data(), 192, 64), o_s0b = pk.put(s0b.data(), 192);
+  int64_t o_s3 = pk.put(s3.data(), 192), o_s3b = pk.put(s3b.data(), 3);
+  int64_t o_out_w = pk.put(W.out_w, 64), o_out_b = pk.put(W.out_b, 1);
+  BlockOff eo[4], dofs[4];
+  for (int i = 0; i < cfg->encoder_layers; ++i) eo[i] = pack_block(pk, W.enc[i]);
+  for (int i = 0; i < cfg->decoder_layers; ++i) dofs[i] = pack_block(pk, W.dec[i]);
+
+  if (cudaMalloc(&h->d_f32, pk.f.size() * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&h->d_f16, pk.h.size() * sizeof(__half)) != cudaSuccess) {
+    set_error("cudaMalloc of the weight buffers failed");
+    s2s_destroy(h);
+    return -1;
+  }
+  cudaMemcpy(h->d_f32, pk.f.data(), pk.f.size() * sizeof(float), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_f16, pk.h.data(), pk.h.size() * sizeof(__half), cudaMemcpyHostToDevice);
+  const float* f = h->d_f32;
+  DevWeights& d = h->dw;
+  d.cfg = *cfg;
+  d.enc_pos = f + o_enc_pos; d.dec_pos = f + o_dec_pos;
+  d.src_t = f + o_src_t; d.src_b = f + o_src_b; d.pre_t = f + o_pre_t; d.pre_b = f + o_pre_b;
+  d.smp0_t = f + o_s0t; d.smp0_b = f + o_s0b; d.smp3_w = f + o_s3; d.smp3_b = f + o_s3b;
+  d.out_w = f + o_out_w; d.out_b = f + o_out_b;
+  for (int i = 0; i < cfg->encoder_layers; ++i) bind_block(d.enc[i], eo[i], f, h->d_f16);
+  for (int i = 0; i < cfg->decoder_layers; ++i) bind_block(d.dec[i], dofs[i], f, h->d_f16);
+  if (tc_init(h->tc, h->dw, device)) {
+    s2s_destroy(h);
+    return -1;
+  }
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    set_error("s2s_create: %s", cudaGetErrorString(e));
+    s2s_destroy(h);
+    return -1;
+  }
+  *out = h;
+  return 0;
+}
+
+void s2s_destroy(s2s_handle h) {
+  if (!h) return;
+  tc_destroy(h->tc);
+  if (h->d_f32) cudaFree(h->d_f32);
+  if (h->d_f16) cudaFree(h->d_f16);
+  delete h;
+}
+
+int64_t s2s_workspace_bytes(s2s_handle h, int64_t n_chunks, int64_t n_reads) {
+  if (!h || n_chunks < 0) return -1;
+  Workspace w;
+  return carve(w, nullptr, h, n_chunks, n_reads, true) + 256;
+}
+
+int s2s_forward_reads(s2s_handle h, const uint8_t* bases_dev, const int64_t* read_offsets_dev,
+                      const int64_t* chunk_offsets_dev, int64_t n_reads, int64_t n_chunks, const s2s_run_opts* opts,
+                      void* workspace_dev, int64_t workspace_bytes, int16_t* raw_out_dev, int64_t* raw_offsets_dev,
+                      const s2s_taps* taps, s2s_stream stream) {
+  if (!h) { set_error("null handle"); return -1; }
+  if (check_opts(opts)) return -1;
+  if (n_reads < 0 || n_chunks < 0) { set_error("negative sizes"); return -1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace w;
+  // 256-byte align the caller's pointer
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<int64_t>(workspace_dev), 256));
+  int64_t need = carve(w, base, h, n_chunks, n_reads, true);
+  if (!workspace_dev || need + (base - static_cast<char*>(workspace_dev)) > workspace_bytes) {
+    set_error("workspace too small: need %lld bytes", (long long)(need + 256));
+    return -1;
+  }
+  if (launch_chunk_map(read_offsets_dev, chunk_offsets_dev, n_reads, n_chunks, h->cfg.seq_kmer, w.chunk_read,
+                       w.chunk_base, w.chunk_nk, st)) return -1;
+  if (run_pipeline(h, bases_dev, nullptr, w, n_chunks, *opts, w.pa, taps, st)) return -1;
+  return launch_compact(w.pa, chunk_offsets_dev, n_reads, n_chunks, opts->digitisation, opts->range, opts->offset_mean,
+                        opts->rna_reverse, w.compact_ws, w.compact_bytes, raw_out_dev, raw_offsets_dev, st);
+}
+
+int s2s_forward_chunks(s2s_handle h, const int8_t* codes_dev, int64_t n_chunks, const s2s_run_opts* opts,
+                       void* workspace_dev, int64_t workspace_bytes, float* pa_out_dev, const s2s_taps* taps,
+                       s2s_stream stream) {
+  if (!h) { set_error("null handle"); return -1; }
+  if (check_opts(opts)) return -1;
+  if (n_chunks < 0 || !codes_dev || !pa_out_dev) { set_error("bad arguments"); return -1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace w;
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<int64_t>(workspace_dev), 256));
+  int64_t need = carve(w, base, h, n_chunks, 0, false);
+  if (!workspace_dev || need + (base - static_cast<char*>(workspace_dev)) > workspace_bytes) {
+    set_error("workspace too small: need %lld bytes", (long long)(need + 256));
+    return -1;
+  }
+  return run_pipeline(h, nullptr, codes_dev, w, n_chunks, *opts, pa_out_dev, taps, st);
+}
+
+int s2s_length_regulate(const float* x_dev, const float* sigma_dev, const int32_t* dur_dev, int64_t n_chunks,
+                        float* out_dev, float* sigma_ext_dev, int32_t* total_dev, s2s_stream stream) {
+  return launch_length_regulate(x_dev, sigma_dev, dur_dev, n_chunks, nullptr, out_dev, S2S_L_DEC, sigma_ext_dev,
+                                total_dev, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int s2s_digitise(const float* pa_dev, int64_t n, float digitisation, float range, float offset_mean, int16_t* raw_dev,
+                 s2s_stream stream) {
+  return launch_digitise(pa_dev, n, digitisation, range, offset_mean, raw_dev, static_cast<cudaStream_t>(stream));
+}
+
+int s2s_compact_reads(const float* pa_dev, const int64_t* chunk_offsets_dev, int64_t n_reads, int64_t n_chunks,
+                      float digitisation, float range, float offset_mean, int32_t rna_reverse, void* workspace_dev,
+                      int64_t workspace_bytes, int16_t* raw_out_dev, int64_t* raw_offsets_dev, s2s_stream stream) {
+  char* base = reinterpret_cast<char*>(align_up(reinterpret_cast<int64_t>(workspace_dev), 256));
+  return launch_compact(pa_dev, chunk_offsets_dev, n_reads, n_chunks, digitisation, range, offset_mean, rna_reverse,
+                        base, workspace_bytes - (base - static_cast<char*>(workspace_dev)), raw_out_dev,
+                        raw_offsets_dev, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+// Internal launcher declarations (C++; the C-ABI lives in include/s2s_b200.h / s2s_api.cu).
+#pragma once
+#include "s2s_common.cuh"
+#include "s2s_weights.h"
+
+namespace s2s {
+
+// Device-resident derived weights, built once by s2s_create().
+struct BlockDev {
+  // fp32, transposed to [K][N] so a warp reads consecutive output columns (SIMT path)
+  const float *wqkv_t, *bqkv;  // [64][192], [192]   (q | k | v)
+  const float *fc_t, *fc_b;    // [64][64]
+  const float *w1_t, *b1;      // [64][256]
+  const float *w2_t, *b2;      // [256][64]
+  const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+  // fp16, K-major [N][K] (PyTorch's own [out][in] order) for the tcgen05 path
+  const __half *wqkv_h;        // [192][64]
+  const __half *fc_h;          // [64][64]
+  const __half *w1_h;          // [256][64]
+  const __half *w2_h;          // [64][256]
+};
+
+struct DevWeights {
+  s2s_config cfg;
+  const float *enc_pos, *dec_pos;     // [16][64], [250][64]
+  const float *src_t, *src_b;         // [5k][64]
+  const float *pre_t, *pre_b;         // [64][64]
+  const float *smp0_t, *smp0_b;       // [64][192], [192]: first layers of conc | rate | noise MLPs
+  const float *smp3_w, *smp3_b;       // [3][64], [3]
+  const float *out_w, *out_b;         // [64], [1]
+  BlockDev enc[4], dec[4];
+};
+
+// ---- k_frontend.cu -------------------------------------------------------------------------
+// chunk -> (read, first base offset, valid k-mers) by binary search in chunk_offsets.
+int launch_chunk_map(const int64_t* read_offsets, const int64_t* chunk_offsets, int64_t n_reads, int64_t n_chunks,
+                     int32_t k, int32_t* chunk_read, int64_t* chunk_base, int32_t* chunk_nk, cudaStream_t st);
+// Tokenise (bases or codes) + src_emb + ReLU + prenet + ReLU -> emb_out; x_enc = emb_out + pos.
+int launch_embed(const DevWeights& w, const uint8_t* bases, const int64_t* chunk_base, const int32_t* chunk_nk,
+                 const int8_t* codes, int64_t n_chunks, float* emb_out, float* x_enc, cudaStream_t st);
+
+// ---- k_simt.cu (fp32 CUDA-core path) --------------------------------------------------------
+enum { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_RES_LN = 2 };
+// Y[M,N] = epi(X[M,K] @ Wt[K,N] + b); RES_LN: Y = LayerNorm(. + R) * g + beta (N must be 64)
+int launch_linear_f32(const float* X, const float* Wt, const float* b, const float* R, const float* g,
+                      const float* beta, float* Y, int64_t M, int K, int N, int epi, cudaStream_t st);
+// softmax(QK^T/sqrt(8))V per (chunk, head); qkv is [rows,192] (q|k|v), out [rows,64].
+// L = 16 (rows_per_chunk 16) or 250 (rows_per_chunk 256: pad rows are neither keys nor written... they are zeroed)
+int launch_attention_f32(const float* qkv, float* out, int64_t n_chunks, int L, int rows_per_chunk, cudaStream_t st);
+
+// ---- k_samplers.cu ---------------------------------------------------------------------------
+// h3 [M,192] = ReLU(first layers) already computed; this applies the 64->1 heads, Softplus, clamps,
+// draws durations and rounds.  Outputs per k-mer: sigma, dur_int (+ optional conc, rate, dur_float taps).
+int launch_sampler_heads(const DevWeights& w, const float* h3, int64_t n_kmers, const s2s_run_opts& o,
+                         float* sigma, int32_t* dur_int, float* conc_tap, float* rate_tap, float* dur_float_tap,
+                         cudaStream_t st);
+
+// ---- k_length_regulate.cu ---------------------------------------------------------------------
+// x_dec[c, t, :] = (t < total ? enc_out[c, j(t), :] : 0) + dec_pos[t]  for t < 250, 0 for the 6 pad rows.
+// dec_pos == nullptr gives the plain LR output with row stride `rows_per_chunk_out` (stage entry point).
+int launch_length_regulate(const float* enc_out, const float* sigma, const int32_t* dur, int64_t n_chunks,
+                           const float* dec_pos, float* x_dec, int rows_per_chunk_out, float* sigma_ext,
+                           int32_t* total, float* lr_tap, cudaStream_t st);
+
+// ---- k_epilogue.cu ----------------------------------------------------------------------------
+// p = ReLU(y . w_out + b); pA = clamp(165 p + noise, 0).  y has 256 rows per chunk, outputs 250 per chunk.
+int launch_out_epilogue(const DevWeights& w, const float* y, const float* sigma_ext, int64_t n_chunks,
+                        const s2s_run_opts& o, float* p_tap, float* pa, cudaStream_t st);
+int launch_digitise(const float* pa, int64_t n, float dig, float range, float offset, int16_t* raw, cudaStream_t st);
+int64_t compact_workspace_bytes(int64_t n_chunks);
+int launch_compact(const float* pa, const int64_t* chunk_offsets, int64_t n_reads, int64_t n_chunks, float dig,
+                   float range, float offset, int rna_reverse, void* ws, int64_t ws_bytes, int16_t* raw,
+                   int64_t* raw_offsets, cudaStream_t st);
+
+}  // namespace s2s

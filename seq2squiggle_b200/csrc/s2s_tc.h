@@ -1,0 +1,31 @@
+// tcgen05 / TMEM / TMA decoder path (S2S_PREC_FP16_TC): declarations shared with s2s_api.cu.
+#pragma once
+#include "s2s_kernels.h"
+
+namespace s2s {
+
+struct TcState {
+  int device = 0;
+  int sm_count = 148;
+  void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled entry point
+};
+
+// Per-sub-batch device buffers of the tensor-core path (carved from the caller's workspace).
+struct TcBuffers {
+  __half* x16 = nullptr;    // [rows,64]  fp16 copy of the residual stream (GEMM A operand)
+  __half* q16 = nullptr;    // [rows,64]
+  __half* k16 = nullptr;    // [rows,64]
+  __half* vt16 = nullptr;   // [chunks][64][256] V transposed (K-major B operand of P.V)
+  __half* o16 = nullptr;    // [rows,64]  attention output (A operand of fc)
+  __half* y16 = nullptr;    // [rows,64]
+  float* y32 = nullptr;     // [rows,64]
+  int32_t* status = nullptr;  // device-side error/timeout flags
+};
+
+void tc_carve(TcBuffers& b, char* base, int64_t& off, int64_t batch_chunks);
+int tc_init(TcState& s, const DevWeights& w, int device);
+void tc_destroy(TcState& s);
+// Runs all decoder layers in place on x32 ([chunks*256,64] fp32 residual stream).
+int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, int64_t n_chunks, cudaStream_t st);
+
+}  // namespace s2s
