@@ -124,6 +124,10 @@ int s2s_forward_chunks(s2s_handle h, const int8_t* codes_dev, int64_t n_chunks, 
                        void* workspace_dev, int64_t workspace_bytes, float* pa_out_dev, const s2s_taps* taps,
                        s2s_stream stream);
 
+/* Synchronises `stream` and returns <0 if any kernel of this handle raised its device-side error word
+ * (a bounded mbarrier wait that timed out) or a CUDA error is pending.  Call before trusting results. */
+int s2s_check(s2s_handle h, s2s_stream stream);
+
 /* Stage entry points (stage-isolated parity tests; same kernels the forward calls use). */
 int s2s_length_regulate(const float* x_dev /*[C,16,64]*/, const float* sigma_dev /*[C,16]*/,
                         const int32_t* dur_dev /*[C,16]*/, int64_t n_chunks, float* out_dev /*[C,250,64]*/,
@@ -135,6 +139,11 @@ int s2s_compact_reads(const float* pa_dev /*[C,250]*/, const int64_t* chunk_offs
                       int64_t n_chunks, float digitisation, float range, float offset_mean, int32_t rna_reverse,
                       void* workspace_dev, int64_t workspace_bytes, int16_t* raw_out_dev, int64_t* raw_offsets_dev,
                       s2s_stream stream);
+
+/* Measurement hook (bench.py roofline leg): enable=1 starts bracketing every launch of the dominant kernel
+ * (k_tc_attention) with CUDA events on the launching stream; enable=0 stops, synchronises and returns the
+ * summed device time, the number of launches and the chunks they covered. */
+int s2s_profile_kernel(s2s_handle h, int enable, double* ms_total, int64_t* launches, int64_t* chunks);
 
 /* Launch counter: number of kernels this library has launched since load (bench.py gpu_launches). */
 int64_t s2s_launch_count(void);

@@ -10,13 +10,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libs2s_b200.so")
 SOURCES = ["s2s_api.cu", "k_frontend.cu", "k_simt.cu", "k_samplers.cu", "k_length_regulate.cu", "k_epilogue.cu",
-           "k_tc_stub.cu"]
+           "k_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared"]
 
 EXPORTS = ["s2s_last_error", "s2s_abi_version", "s2s_weights_count", "s2s_create", "s2s_destroy",
            "s2s_workspace_bytes", "s2s_chunks_of_read", "s2s_forward_reads", "s2s_forward_chunks",
-           "s2s_length_regulate", "s2s_digitise", "s2s_compact_reads", "s2s_launch_count"]
+           "s2s_check", "s2s_length_regulate", "s2s_digitise", "s2s_compact_reads", "s2s_profile_kernel", "s2s_launch_count"]
 
 
 class S2SConfig(C.Structure):
@@ -92,6 +92,8 @@ def load() -> C.CDLL:
                                       C.POINTER(S2STaps), vp]
     lib.s2s_forward_chunks.restype = C.c_int
     lib.s2s_forward_chunks.argtypes = [vp, vp, i64, C.POINTER(S2SRunOpts), vp, i64, vp, C.POINTER(S2STaps), vp]
+    lib.s2s_check.restype = C.c_int
+    lib.s2s_check.argtypes = [vp, vp]
     lib.s2s_length_regulate.restype = C.c_int
     lib.s2s_length_regulate.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
     lib.s2s_digitise.restype = C.c_int

@@ -1,0 +1,688 @@
+// Decoder FFT blocks on the 5th-generation tensor cores (S2S_PREC_FP16_TC).
+//
+// layers.py:44-142 at L = 250 (256 rows per chunk in HBM).  fp16 operands (the reference's own GPU dtype:
+// Lightning "16-mixed", inference.py:404), fp32 accumulation in TMEM, fp32 softmax / LayerNorm / residual.
+// Four kernels per layer, all tcgen05.mma (kind::f16, M=128) fed by TMA into 128-byte-swizzled K-major
+// shared-memory tiles, accumulators in TMEM, epilogues by tcgen05.ld with one thread per row:
+//   k_tc_qkv        Q|K|V = X Wqkv^T + b          -> Q16 [rows,64], Kmask [rows,128], V^T [chunk,8,16,256]
+//   k_tc_attention  per (chunk, 4 heads): S = Q_h K_h^T (one N=256,K=16 MMA), row softmax in registers,
+//                   P (fp16) written back to TMEM over S, O = P V_h (16 TS MMAs, A operand from TMEM)
+//   k_tc_fc_ln      Y = LayerNorm(O Wfc^T + b + X)
+//   k_tc_ffn_ln     X' = LayerNorm(relu(Y W1^T + b1) W2^T + b2 + Y); the 256-wide hidden never leaves TMEM
+//
+// d_k = 8 but the fp16 MMA has K = 16: K is stored "masked" (head h's 8 values in the half of a 32-byte slot
+// that lines up with head h inside the 32-byte Q slice of heads {2i,2i+1}; the other half is zero), so one
+// K=16 MMA computes exactly q_h . k_h.  d_v = 8 but N >= 16 for M = 128: V_h^T is padded to 16 rows with a row
+// of ones, so column 8 of O is the softmax denominator (sum of the ROUNDED probabilities) for free.
+#include "s2s_tc.h"
+#include "tc_host.h"
+#include "tc_prims.cuh"
+
+namespace s2s {
+using namespace tc;
+
+namespace {
+
+constexpr uint32_t kWaitLimit = 1u << 22;
+constexpr int kSlab = 128 * 128;  // bytes of one [128 rows x 128 B] tile
+
+// status codes written on a barrier timeout
+enum { kErrQkvLoad = 11, kErrQkvMma = 12, kErrAttLoad = 21, kErrAttS = 22, kErrAttO = 23, kErrFcLoad = 31,
+       kErrFcMma = 32, kErrFfnLoad = 41, kErrFfnMma1 = 42, kErrFfnMma2 = 43 };
+
+__device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, int* status, volatile int* s_abort, int code) {
+  if (*s_abort) return false;
+  for (uint32_t i = 0; i < kWaitLimit; ++i)
+    if (mbar_try_wait(bar, parity)) return true;
+  *s_abort = 1;
+  atomicExch(status, code);
+  return false;
+}
+
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// LayerNorm over the 64 values a thread holds for its row (biased variance, eps 1e-5), then write the
+// fp32 row (next residual) and the fp16 row (next GEMM operand).
+__device__ __forceinline__ void layernorm_store(float (&v)[64], const float* s_g, const float* s_b,
+                                                float* __restrict__ out32, __half* __restrict__ out16) {
+  float mean = 0.f;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) mean += v[i];
+  mean *= (1.f / 64.f);
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) { float d = v[i] - mean; var = fmaf(d, d, var); }
+  const float rstd = 1.0f / sqrtf(var * (1.f / 64.f) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = (v[i] - mean) * rstd * s_g[i] + s_b[i];
+#pragma unroll
+  for (int i = 0; i < 64; i += 4)
+    *reinterpret_cast<float4*>(out32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+#pragma unroll
+  for (int i = 0; i < 64; i += 8)
+    *reinterpret_cast<uint4*>(out16 + i) = make_uint4(pack_half2(v[i], v[i + 1]), pack_half2(v[i + 2], v[i + 3]),
+                                                       pack_half2(v[i + 4], v[i + 5]), pack_half2(v[i + 6], v[i + 7]));
+}
+
+// =================================================================================================
+// G1: QKV projection.  128 threads, 2 CTAs / SM (TMEM 256 columns each).
+// =================================================================================================
+__global__ void __launch_bounds__(128) k_tc_qkv(const __grid_constant__ CUtensorMap tmX,
+                                                const __grid_constant__ CUtensorMap tmW,
+                                                const float* __restrict__ bias, __half* __restrict__ q16,
+                                                __half* __restrict__ kmask, __half* __restrict__ vt, int n_tiles,
+                                                int* status) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_w, bar_a[2], bar_mma;
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_abort;
+  __shared__ float s_bias[192];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sW = smem;                 // [192 x 128 B]
+  uint8_t* sA = smem + 192 * 128;     // 2 x [128 x 128 B]
+  const int tid = threadIdx.x, warp = tid >> 5;
+  __shared__ int s_go;
+  if (tid == 0) s_go = (*status == 0);
+  __syncthreads();
+  if (!s_go) return;  // an earlier kernel timed out: unwind quickly (uniform per CTA)
+  if (warp == 0) tmem_alloc<256>(&s_tmem);
+  if (tid == 0) {
+    mbar_init(&bar_w, 1); mbar_init(&bar_a[0], 1); mbar_init(&bar_a[1], 1); mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+    s_abort = 0;
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW);
+  }
+  for (int i = tid; i < 192; i += 128) s_bias[i] = bias[i];
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s_tmem;
+  int tile = blockIdx.x;
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar_w, 192 * 128);
+    tma_load_2d(sW, &tmW, &bar_w, 0, 0);
+    if (tile < n_tiles) {
+      mbar_arrive_expect_tx(&bar_a[0], kSlab);
+      tma_load_2d(sA, &tmX, &bar_a[0], 0, tile * 128);
+    }
+  }
+  wait_bar(&bar_w, 0, status, &s_abort, kErrQkvLoad);
+  const uint32_t idesc = umma_idesc(128, 192, kFmtF16);
+  for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int next = tile + gridDim.x;
+    if (tid == 0 && next < n_tiles) {  // prefetch the next A tile into the other buffer (its MMA finished last iteration)
+      mbar_arrive_expect_tx(&bar_a[buf ^ 1], kSlab);
+      tma_load_2d(sA + (buf ^ 1) * kSlab, &tmX, &bar_a[buf ^ 1], 0, next * 128);
+    }
+    wait_bar(&bar_a[buf], (it >> 1) & 1, status, &s_abort, kErrQkvLoad);
+    tcgen05_fence_after();
+    if (tid == 0) {
+      const uint32_t a0 = smem_u32(sA + buf * kSlab), b0 = smem_u32(sW);
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+        umma_f16_ss(tmem, umma_desc_k_sw128(a0 + s * 32), umma_desc_k_sw128(b0 + s * 32), idesc, s > 0);
+      umma_commit(&bar_mma);
+    }
+    wait_bar(&bar_mma, it & 1, status, &s_abort, kErrQkvMma);
+    tcgen05_fence_after();
+    const int64_t row = (int64_t)tile * 128 + tid;
+    const int64_t chunk = tile >> 1;
+    const int t = (tile & 1) * 128 + tid;  // key index inside the chunk
+    const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
+    uint32_t r[32];
+    // ---- Q: columns 0..63 -> fp16 row-major
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      tmem_ld_32x32(lane_addr + c0, r);
+      tmem_wait_ld();
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        pk[i] = pack_half2(__uint_as_float(r[2 * i]) + s_bias[c0 + 2 * i], __uint_as_float(r[2 * i + 1]) + s_bias[c0 + 2 * i + 1]);
+      uint4* dst = reinterpret_cast<uint4*>(q16 + row * 64 + c0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    }
+    // ---- K: columns 64..127 -> masked 32-byte slot per head: [data|0] for even heads, [0|data] for odd heads
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      tmem_ld_32x32(lane_addr + 64 + c0, r);
+      tmem_wait_ld();
+      uint4* dst = reinterpret_cast<uint4*>(kmask + row * 128 + c0 * 2);  // head h slot at element offset 16h
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          pk[i] = pack_half2(__uint_as_float(r[8 * hh + 2 * i]) + s_bias[64 + c0 + 8 * hh + 2 * i],
+                             __uint_as_float(r[8 * hh + 2 * i + 1]) + s_bias[64 + c0 + 8 * hh + 2 * i + 1]);
+        const uint4 data = make_uint4(pk[0], pk[1], pk[2], pk[3]), zero = make_uint4(0u, 0u, 0u, 0u);
+        dst[2 * hh] = (hh & 1) ? zero : data;
+        dst[2 * hh + 1] = (hh & 1) ? data : zero;
+      }
+    }
+    // ---- V: columns 128..191 -> transposed, padded to 16 rows per head (row 8 = ones, rows 9..15 = 0)
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      tmem_ld_32x32(lane_addr + 128 + c0, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        const int h = (c0 >> 3) + hh;
+        __half* base = vt + ((chunk * 8 + h) * 16) * 256 + t;
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
+          base[d * 256] = __float2half_rn(__uint_as_float(r[8 * hh + d]) + s_bias[128 + c0 + 8 * hh + d]);
+        base[8 * 256] = __float2half_rn(1.0f);
+#pragma unroll
+        for (int d = 9; d < 16; ++d) base[d * 256] = __float2half_rn(0.0f);
+      }
+    }
+    tcgen05_fence_before();
+    __syncthreads();  // every thread has drained its TMEM reads before the next MMA overwrites the accumulator
+    tcgen05_fence_after();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+// =================================================================================================
+// ATT: attention core for one (chunk, group of 4 heads).  128 threads = 128 query rows of a tile.
+// =================================================================================================
+__global__ void __launch_bounds__(128) k_tc_attention(const __grid_constant__ CUtensorMap tmQ,
+                                                      const __grid_constant__ CUtensorMap tmK,
+                                                      const __grid_constant__ CUtensorMap tmV,
+                                                      __half* __restrict__ o16, int n_units, int* status) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_load, bar_s, bar_o;
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_abort;
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sQ = smem;                  // 2 x [128 x 128 B]   (all 8 heads of both query tiles)
+  uint8_t* sK = smem + 2 * kSlab;      // [256 keys x 128 B]  (masked K of this head group)
+  uint8_t* sV = smem + 4 * kSlab;      // 4 key slabs x [64 rows (4 heads x 16) x 128 B]
+  const int tid = threadIdx.x, warp = tid >> 5;
+  __shared__ int s_go;
+  if (tid == 0) s_go = (*status == 0);
+  __syncthreads();
+  if (!s_go) return;  // an earlier kernel timed out: unwind quickly (uniform per CTA)
+  if (warp == 0) tmem_alloc<256>(&s_tmem);
+  if (tid == 0) {
+    mbar_init(&bar_load, 1); mbar_init(&bar_s, 1); mbar_init(&bar_o, 1);
+    fence_mbar_init();
+    s_abort = 0;
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s_tmem;
+  const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
+  const uint32_t idesc_s = umma_idesc(128, 256, kFmtF16), idesc_o = umma_idesc(128, 16, kFmtF16);
+  const float kScale = 0.35355339059327373f * 1.4426950408889634f;  // log2(e) / sqrt(d_k)
+  uint32_t ph_load = 0, ph_s = 0, ph_o = 0;
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int chunk = unit >> 1, g = unit & 1;
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&bar_load, 6 * kSlab);
+      tma_load_2d(sQ, &tmQ, &bar_load, 0, chunk * 256);
+      tma_load_2d(sQ + kSlab, &tmQ, &bar_load, 0, chunk * 256 + 128);
+      tma_load_2d(sK, &tmK, &bar_load, g * 64, chunk * 256);
+#pragma unroll
+      for (int s = 0; s < 4; ++s) tma_load_2d(sV + s * 8192, &tmV, &bar_load, s * 64, (chunk * 8 + g * 4) * 16);
+    }
+    wait_bar(&bar_load, ph_load, status, &s_abort, kErrAttLoad);
+    ph_load ^= 1;
+    tcgen05_fence_after();
+    for (int hh = 0; hh < 4; ++hh) {
+      const int h = g * 4 + hh;
+      for (int tile = 0; tile < 2; ++tile) {
+        if (tid == 0) {  // S = Q_h K_h^T : one MMA, N = 256 keys, K = 16 (8 real + 8 masked)
+          umma_f16_ss(tmem, umma_desc_k_sw128(smem_u32(sQ + tile * kSlab) + (h >> 1) * 32),
+                      umma_desc_k_sw128(smem_u32(sK) + hh * 32), idesc_s, 0);
+          umma_commit(&bar_s);
+        }
+        wait_bar(&bar_s, ph_s, status, &s_abort, kErrAttS);
+        ph_s ^= 1;
+        tcgen05_fence_after();
+        uint32_t r[32];
+        // pass 1: row maximum over the 250 real keys
+        float m = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          tmem_ld_32x32(lane_addr + c * 32, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c < 7 || i < S2S_L_DEC - 224) m = fmaxf(m, __uint_as_float(r[i]));
+        }
+        const float mneg = -m * kScale;
+        // pass 2: P = exp2(S*c - m*c) rounded to fp16, written over S (chunk c -> columns [16c,16c+16))
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          tmem_ld_32x32(lane_addr + c * 32, r);
+          tmem_wait_ld();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), kScale, mneg));
+            float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), kScale, mneg));
+            if (c == 7 && 2 * i >= S2S_L_DEC - 224) p0 = 0.f;       // keys 250..255 are padding
+            if (c == 7 && 2 * i + 1 >= S2S_L_DEC - 224) p1 = 0.f;
+            pk[i] = pack_half2(p0, p1);
+          }
+          tmem_st_32x16(lane_addr + c * 16, pk);
+        }
+        tmem_wait_st();
+        tcgen05_fence_before();
+        __syncthreads();
+        if (tid == 0) {  // O = P V_h : 16 K-steps of 16 keys, A operand straight from TMEM
+          tcgen05_fence_after();
+          const uint32_t vb = smem_u32(sV) + hh * 2048;
+#pragma unroll
+          for (int s = 0; s < 16; ++s)
+            umma_f16_ts(tmem + 128, tmem + 8 * s, umma_desc_k_sw128(vb + (s >> 2) * 8192 + (s & 3) * 32), idesc_o, s > 0);
+          umma_commit(&bar_o);
+        }
+        wait_bar(&bar_o, ph_o, status, &s_abort, kErrAttO);
+        ph_o ^= 1;
+        tcgen05_fence_after();
+        uint32_t o[16];
+        tmem_ld_32x16(lane_addr + 128, o);
+        tmem_wait_ld();
+        const float inv = 1.0f / __uint_as_float(o[8]);  // column 8 = sum of the rounded probabilities
+        const int64_t row = (int64_t)chunk * 256 + tile * 128 + tid;
+        *reinterpret_cast<uint4*>(o16 + row * 64 + h * 8) =
+            make_uint4(pack_half2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv),
+                       pack_half2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv),
+                       pack_half2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv),
+                       pack_half2(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv));
+        tcgen05_fence_before();
+        __syncthreads();  // O has been read everywhere before the next S MMA reuses the columns
+        tcgen05_fence_after();
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+// =================================================================================================
+// G2: Y = LayerNorm(O Wfc^T + b + X).  128 threads, TMEM 64 columns.
+// =================================================================================================
+__global__ void __launch_bounds__(128) k_tc_fc_ln(const __grid_constant__ CUtensorMap tmA,
+                                                  const __grid_constant__ CUtensorMap tmW,
+                                                  const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                  const float* __restrict__ beta, const float* __restrict__ res,
+                                                  float* __restrict__ y32, __half* __restrict__ y16, int n_tiles,
+                                                  int* status) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_w, bar_a[2], bar_mma;
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_abort;
+  __shared__ float s_bias[64], s_g[64], s_b[64];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sW = smem;             // [64 x 128 B]
+  uint8_t* sA = smem + 64 * 128;  // 2 x [128 x 128 B]  (8 KB offset keeps 1024-byte alignment)
+  const int tid = threadIdx.x, warp = tid >> 5;
+  __shared__ int s_go;
+  if (tid == 0) s_go = (*status == 0);
+  __syncthreads();
+  if (!s_go) return;  // an earlier kernel timed out: unwind quickly (uniform per CTA)
+  if (warp == 0) tmem_alloc<64>(&s_tmem);
+  if (tid == 0) {
+    mbar_init(&bar_w, 1); mbar_init(&bar_a[0], 1); mbar_init(&bar_a[1], 1); mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+    s_abort = 0;
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW);
+  }
+  if (tid < 64) { s_bias[tid] = bias[tid]; s_g[tid] = gamma[tid]; s_b[tid] = beta[tid]; }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s_tmem;
+  int tile = blockIdx.x;
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar_w, 64 * 128);
+    tma_load_2d(sW, &tmW, &bar_w, 0, 0);
+    if (tile < n_tiles) {
+      mbar_arrive_expect_tx(&bar_a[0], kSlab);
+      tma_load_2d(sA, &tmA, &bar_a[0], 0, tile * 128);
+    }
+  }
+  wait_bar(&bar_w, 0, status, &s_abort, kErrFcLoad);
+  const uint32_t idesc = umma_idesc(128, 64, kFmtF16);
+  for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int next = tile + gridDim.x;
+    if (tid == 0 && next < n_tiles) {
+      mbar_arrive_expect_tx(&bar_a[buf ^ 1], kSlab);
+      tma_load_2d(sA + (buf ^ 1) * kSlab, &tmA, &bar_a[buf ^ 1], 0, next * 128);
+    }
+    wait_bar(&bar_a[buf], (it >> 1) & 1, status, &s_abort, kErrFcLoad);
+    tcgen05_fence_after();
+    if (tid == 0) {
+      const uint32_t a0 = smem_u32(sA + buf * kSlab), b0 = smem_u32(sW);
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+        umma_f16_ss(tmem, umma_desc_k_sw128(a0 + s * 32), umma_desc_k_sw128(b0 + s * 32), idesc, s > 0);
+      umma_commit(&bar_mma);
+    }
+    const int64_t row = (int64_t)tile * 128 + tid;
+    float v[64];
+    {  // residual row while the MMA runs
+      const float4* rp = reinterpret_cast<const float4*>(res + row * 64);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float4 x = rp[i];
+        v[4 * i] = x.x + s_bias[4 * i]; v[4 * i + 1] = x.y + s_bias[4 * i + 1];
+        v[4 * i + 2] = x.z + s_bias[4 * i + 2]; v[4 * i + 3] = x.w + s_bias[4 * i + 3];
+      }
+    }
+    wait_bar(&bar_mma, it & 1, status, &s_abort, kErrFcMma);
+    tcgen05_fence_after();
+    const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
+    uint32_t r[32];
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      tmem_ld_32x32(lane_addr + c0, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[c0 + i] += __uint_as_float(r[i]);
+    }
+    tcgen05_fence_before();
+    layernorm_store(v, s_g, s_b, y32 + row * 64, y16 + row * 64);
+    __syncthreads();
+    tcgen05_fence_after();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<64>(tmem);
+}
+
+// =================================================================================================
+// G3: X' = LayerNorm(relu(Y W1^T + b1) W2^T + b2 + Y).  128 threads, 2 CTAs / SM, TMEM 256 columns:
+//     D1 [0,256) fp32 -> H fp16 packed over [0,128) -> D2 [128,192).
+// =================================================================================================
+__global__ void __launch_bounds__(128) k_tc_ffn_ln(const __grid_constant__ CUtensorMap tmA,
+                                                   const __grid_constant__ CUtensorMap tmW1,
+                                                   const __grid_constant__ CUtensorMap tmW2,
+                                                   const float* __restrict__ b1, const float* __restrict__ b2,
+                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                   const float* __restrict__ res, float* __restrict__ x32,
+                                                   __half* __restrict__ x16, int n_tiles, int* status) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_w, bar_a[2], bar_m1, bar_m2;
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_abort;
+  __shared__ float s_b1[256], s_b2[64], s_g[64], s_b[64];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sW1 = smem;                  // [256 x 128 B]
+  uint8_t* sW2 = smem + 256 * 128;      // 4 K-slabs x [64 x 128 B]
+  uint8_t* sA = smem + 2 * 256 * 128;   // 2 x [128 x 128 B]
+  const int tid = threadIdx.x, warp = tid >> 5;
+  __shared__ int s_go;
+  if (tid == 0) s_go = (*status == 0);
+  __syncthreads();
+  if (!s_go) return;  // an earlier kernel timed out: unwind quickly (uniform per CTA)
+  if (warp == 0) tmem_alloc<256>(&s_tmem);
+  if (tid == 0) {
+    mbar_init(&bar_w, 1); mbar_init(&bar_a[0], 1); mbar_init(&bar_a[1], 1); mbar_init(&bar_m1, 1); mbar_init(&bar_m2, 1);
+    fence_mbar_init();
+    s_abort = 0;
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
+  }
+  for (int i = tid; i < 256; i += 128) s_b1[i] = b1[i];
+  if (tid < 64) { s_b2[tid] = b2[tid]; s_g[tid] = gamma[tid]; s_b[tid] = beta[tid]; }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s_tmem;
+  int tile = blockIdx.x;
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar_w, 2 * 256 * 128);
+    tma_load_2d(sW1, &tmW1, &bar_w, 0, 0);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) tma_load_2d(sW2 + s * 8192, &tmW2, &bar_w, s * 64, 0);
+    if (tile < n_tiles) {
+      mbar_arrive_expect_tx(&bar_a[0], kSlab);
+      tma_load_2d(sA, &tmA, &bar_a[0], 0, tile * 128);
+    }
+  }
+  wait_bar(&bar_w, 0, status, &s_abort, kErrFfnLoad);
+  const uint32_t idesc1 = umma_idesc(128, 256, kFmtF16), idesc2 = umma_idesc(128, 64, kFmtF16);
+  const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
+  for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int next = tile + gridDim.x;
+    if (tid == 0 && next < n_tiles) {
+      mbar_arrive_expect_tx(&bar_a[buf ^ 1], kSlab);
+      tma_load_2d(sA + (buf ^ 1) * kSlab, &tmA, &bar_a[buf ^ 1], 0, next * 128);
+    }
+    wait_bar(&bar_a[buf], (it >> 1) & 1, status, &s_abort, kErrFfnLoad);
+    tcgen05_fence_after();
+    if (tid == 0) {
+      const uint32_t a0 = smem_u32(sA + buf * kSlab), b0 = smem_u32(sW1);
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+        umma_f16_ss(tmem, umma_desc_k_sw128(a0 + s * 32), umma_desc_k_sw128(b0 + s * 32), idesc1, s > 0);
+      umma_commit(&bar_m1);
+    }
+    wait_bar(&bar_m1, it & 1, status, &s_abort, kErrFfnMma1);
+    tcgen05_fence_after();
+    uint32_t r[32];
+    // hidden = relu(D1 + b1) -> fp16, packed over the columns already consumed
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+      tmem_ld_32x32(lane_addr + c * 32, r);
+      tmem_wait_ld();
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        pk[i] = pack_half2(fmaxf(__uint_as_float(r[2 * i]) + s_b1[c * 32 + 2 * i], 0.f),
+                           fmaxf(__uint_as_float(r[2 * i + 1]) + s_b1[c * 32 + 2 * i + 1], 0.f));
+      tmem_st_32x16(lane_addr + c * 16, pk);
+    }
+    tmem_wait_st();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tcgen05_fence_after();
+      const uint32_t w2 = smem_u32(sW2);
+#pragma unroll
+      for (int s = 0; s < 16; ++s)
+        umma_f16_ts(tmem + 128, tmem + 8 * s, umma_desc_k_sw128(w2 + (s >> 2) * 8192 + (s & 3) * 32), idesc2, s > 0);
+      umma_commit(&bar_m2);
+    }
+    const int64_t row = (int64_t)tile * 128 + tid;
+    float v[64];
+    {
+      const float4* rp = reinterpret_cast<const float4*>(res + row * 64);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float4 x = rp[i];
+        v[4 * i] = x.x + s_b2[4 * i]; v[4 * i + 1] = x.y + s_b2[4 * i + 1];
+        v[4 * i + 2] = x.z + s_b2[4 * i + 2]; v[4 * i + 3] = x.w + s_b2[4 * i + 3];
+      }
+    }
+    wait_bar(&bar_m2, it & 1, status, &s_abort, kErrFfnMma2);
+    tcgen05_fence_after();
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      tmem_ld_32x32(lane_addr + 128 + c0, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[c0 + i] += __uint_as_float(r[i]);
+    }
+    tcgen05_fence_before();
+    layernorm_store(v, s_g, s_b, x32 + row * 64, x16 + row * 64);
+    __syncthreads();
+    tcgen05_fence_after();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+__global__ void k_f32_to_f16(const float* __restrict__ x, __half* __restrict__ y, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
+  }
+}
+
+constexpr int kSmemQkv = 81920;             // 57 KB used; padded so at most 2 CTAs (2 x 256 TMEM columns) share an SM
+constexpr int kSmemAtt = 6 * kSlab + 1024;  // 97 KB -> 2 CTAs / SM
+constexpr int kSmemFc = 64 * 128 + 2 * kSlab + 1024;
+constexpr int kSmemFfn = 6 * kSlab + 1024;
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------
+void tc_carve(TcBuffers& b, char* base, int64_t& off, int64_t bc) {
+  auto take = [&](int64_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off += align_up(bytes, 1024);
+    return p;
+  };
+  const int64_t rows = bc * S2S_L_DEC_PAD;
+  b.x16 = reinterpret_cast<__half*>(take(rows * 64 * 2));
+  b.q16 = reinterpret_cast<__half*>(take(rows * 64 * 2));
+  b.k16 = reinterpret_cast<__half*>(take(rows * 128 * 2));
+  b.vt16 = reinterpret_cast<__half*>(take(bc * 8 * 16 * 256 * 2));
+  b.o16 = reinterpret_cast<__half*>(take(rows * 64 * 2));
+  b.y16 = reinterpret_cast<__half*>(take(rows * 64 * 2));
+  b.y32 = reinterpret_cast<float*>(take(rows * 64 * 4));
+}
+
+int tc_init(TcState& s, const DevWeights& w, int device) {
+  s.device = device;
+  cudaDeviceProp prop;
+  S2S_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  s.sm_count = prop.multiProcessorCount;
+  s.encode_tiled = reinterpret_cast<void*>(get_encode_tiled());
+  if (!s.encode_tiled) {
+    set_error("cuTensorMapEncodeTiled driver entry point not found");
+    return -1;
+  }
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_qkv, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemQkv));
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt));
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFc));
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_ffn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
+  (void)w;
+  S2S_CUDA_OK(cudaMalloc(&s.d_status, 256));
+  S2S_CUDA_OK(cudaMemset(s.d_status, 0, 256));
+  return 0;
+}
+
+void tc_destroy(TcState& s) {
+  if (s.d_status) cudaFree(s.d_status);
+  s.d_status = nullptr;
+}
+
+int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, int64_t n_chunks, cudaStream_t st) {
+  if (n_chunks == 0) return 0;
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(s.encode_tiled);
+  const uint64_t rows = (uint64_t)n_chunks * S2S_L_DEC_PAD;
+  const int n_tiles = (int)(rows / 128);
+  const CUtensorMapDataType f16 = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  CUtensorMap tmX, tmQ, tmK, tmV, tmO, tmY;
+  bool ok = make_tmap_2d(enc, &tmX, b.x16, f16, 2, rows, 64, 128, 64, sw) &&
+            make_tmap_2d(enc, &tmQ, b.q16, f16, 2, rows, 64, 128, 64, sw) &&
+            make_tmap_2d(enc, &tmK, b.k16, f16, 2, rows, 128, 256, 64, sw) &&
+            make_tmap_2d(enc, &tmV, b.vt16, f16, 2, (uint64_t)n_chunks * 128, 256, 64, 64, sw) &&
+            make_tmap_2d(enc, &tmO, b.o16, f16, 2, rows, 64, 128, 64, sw) &&
+            make_tmap_2d(enc, &tmY, b.y16, f16, 2, rows, 64, 128, 64, sw);
+  if (!ok) {
+    set_error("cuTensorMapEncodeTiled failed for an activation tensor");
+    return -1;
+  }
+  {  // fp16 copy of the decoder input (the fp32 residual stream stays the master copy)
+    const int64_t n4 = (int64_t)rows * 16;
+    int64_t blocks = ceil_div(n4, 256);
+    if (blocks > s.sm_count * 16) blocks = s.sm_count * 16;
+    k_f32_to_f16<<<(unsigned)blocks, 256, 0, st>>>(x32, b.x16, n4);
+    S2S_LAUNCH_CHECK();
+  }
+  const int grid2 = n_tiles < 2 * s.sm_count ? n_tiles : 2 * s.sm_count;
+  const int grid4 = n_tiles < 4 * s.sm_count ? n_tiles : 4 * s.sm_count;
+  const int n_units = (int)(2 * n_chunks);
+  const int grid_att = n_units < 2 * s.sm_count ? n_units : 2 * s.sm_count;
+  for (int l = 0; l < w.cfg.decoder_layers; ++l) {
+    const BlockDev& bl = w.dec[l];
+    CUtensorMap tmWqkv, tmWfc, tmW1, tmW2;
+    ok = make_tmap_2d(enc, &tmWqkv, bl.wqkv_h, f16, 2, 192, 64, 192, 64, sw) &&
+         make_tmap_2d(enc, &tmWfc, bl.fc_h, f16, 2, 64, 64, 64, 64, sw) &&
+         make_tmap_2d(enc, &tmW1, bl.w1_h, f16, 2, 256, 64, 256, 64, sw) &&
+         make_tmap_2d(enc, &tmW2, bl.w2_h, f16, 2, 64, 256, 64, 64, sw);
+    if (!ok) {
+      set_error("cuTensorMapEncodeTiled failed for a weight tensor");
+      return -1;
+    }
+    k_tc_qkv<<<grid2, 128, kSmemQkv, st>>>(tmX, tmWqkv, bl.bqkv, b.q16, b.k16, b.vt16, n_tiles, s.d_status);
+    S2S_LAUNCH_CHECK();
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (s.prof_on) {
+      cudaEventCreate(&e0); cudaEventCreate(&e1);
+      cudaEventRecord(e0, st);
+    }
+    k_tc_attention<<<grid_att, 128, kSmemAtt, st>>>(tmQ, tmK, tmV, b.o16, n_units, s.d_status);
+    S2S_LAUNCH_CHECK();
+    if (s.prof_on) {
+      cudaEventRecord(e1, st);
+      s.prof_events.push_back(e0); s.prof_events.push_back(e1);
+      s.prof_chunks += n_chunks;
+    }
+    k_tc_fc_ln<<<grid4, 128, kSmemFc, st>>>(tmO, tmWfc, bl.fc_b, bl.ln1_w, bl.ln1_b, x32, b.y32, b.y16, n_tiles, s.d_status);
+    S2S_LAUNCH_CHECK();
+    k_tc_ffn_ln<<<grid2, 128, kSmemFfn, st>>>(tmY, tmW1, tmW2, bl.b1, bl.b2, bl.ln2_w, bl.ln2_b, b.y32, x32, b.x16,
+                                              n_tiles, s.d_status);
+    S2S_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int tc_profile(TcState& s, int enable, double* ms_total, int64_t* launches, int64_t* chunks) {
+  if (enable) {
+    s.prof_on = true;
+    s.prof_chunks = 0;
+    return 0;
+  }
+  s.prof_on = false;
+  S2S_CUDA_OK(cudaDeviceSynchronize());
+  double tot = 0;
+  for (size_t i = 0; i + 1 < s.prof_events.size(); i += 2) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s.prof_events[i], s.prof_events[i + 1]);
+    tot += ms;
+    cudaEventDestroy(s.prof_events[i]);
+    cudaEventDestroy(s.prof_events[i + 1]);
+  }
+  if (ms_total) *ms_total = tot;
+  if (launches) *launches = (int64_t)(s.prof_events.size() / 2);
+  if (chunks) *chunks = s.prof_chunks;
+  s.prof_events.clear();
+  return 0;
+}
+
+int tc_check_status(TcState& s, cudaStream_t st) {
+  int32_t v = 0;
+  S2S_CUDA_OK(cudaStreamSynchronize(st));
+  S2S_CUDA_OK(cudaMemcpy(&v, s.d_status, 4, cudaMemcpyDeviceToHost));
+  if (v != 0) {
+    cudaMemset(s.d_status, 0, 4);
+    set_error("tensor-core decoder: mbarrier wait timed out (kernel code %d); results are invalid", v);
+    return -1;
+  }
+  return 0;
+}
+
+}  // namespace s2s

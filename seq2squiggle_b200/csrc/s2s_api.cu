@@ -412,6 +412,20 @@ int s2s_forward_chunks(s2s_handle h, const int8_t* codes_dev, int64_t n_chunks, 
   return run_pipeline(h, nullptr, codes_dev, w, n_chunks, *opts, pa_out_dev, taps, st);
 }
 
+int s2s_check(s2s_handle h, s2s_stream stream) {
+  if (!h) { set_error("null handle"); return -1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tc_check_status(h->tc, st)) return -1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("CUDA error: %s", cudaGetErrorString(e)); return -1; }
+  return 0;
+}
+
+int s2s_profile_kernel(s2s_handle h, int enable, double* ms_total, int64_t* launches, int64_t* chunks) {
+  if (!h) { set_error("null handle"); return -1; }
+  return tc_profile(h->tc, enable, ms_total, launches, chunks);
+}
+
 int s2s_length_regulate(const float* x_dev, const float* sigma_dev, const int32_t* dur_dev, int64_t n_chunks,
                         float* out_dev, float* sigma_ext_dev, int32_t* total_dev, s2s_stream stream) {
   return launch_length_regulate(x_dev, sigma_dev, dur_dev, n_chunks, nullptr, out_dev, S2S_L_DEC, sigma_ext_dev,

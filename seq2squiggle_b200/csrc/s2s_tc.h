@@ -1,5 +1,7 @@
 // tcgen05 / TMEM / TMA decoder path (S2S_PREC_FP16_TC): declarations shared with s2s_api.cu.
 #pragma once
+#include <vector>
+
 #include "s2s_kernels.h"
 
 namespace s2s {
@@ -8,6 +10,11 @@ struct TcState {
   int device = 0;
   int sm_count = 148;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled entry point
+  int32_t* d_status = nullptr;   // device word set by a kernel whose mbarrier wait timed out
+  // optional CUDA-event bracketing of the attention launches (bench.py roofline leg)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_events;   // start/stop pairs
+  int64_t prof_chunks = 0;
 };
 
 // Per-sub-batch device buffers of the tensor-core path (carved from the caller's workspace).
@@ -19,13 +26,15 @@ struct TcBuffers {
   __half* o16 = nullptr;    // [rows,64]  attention output (A operand of fc)
   __half* y16 = nullptr;    // [rows,64]
   float* y32 = nullptr;     // [rows,64]
-  int32_t* status = nullptr;  // device-side error/timeout flags
 };
 
 void tc_carve(TcBuffers& b, char* base, int64_t& off, int64_t batch_chunks);
 int tc_init(TcState& s, const DevWeights& w, int device);
 void tc_destroy(TcState& s);
 // Runs all decoder layers in place on x32 ([chunks*256,64] fp32 residual stream).
+int tc_profile(TcState& s, int enable, double* ms_total, int64_t* launches, int64_t* chunks);
+// Synchronises the stream and reports a device-side barrier timeout, if any.
+int tc_check_status(TcState& s, cudaStream_t st);
 int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, int64_t n_chunks, cudaStream_t st);
 
 }  // namespace s2s

@@ -151,6 +151,11 @@ class Engine:
             bases, ro, co = bases.pin_memory(), ro.pin_memory(), co.pin_memory()
         return bases, ro, co
 
+    def check(self):
+        """Synchronise and fail loudly if a kernel raised its device-side error word (bounded barrier wait)."""
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.s2s_check(self.handle, st), "s2s_check")
+
     def forward_reads_device(self, bases: torch.Tensor, read_off: torch.Tensor, chunk_off: torch.Tensor,
                              n_reads: int, n_chunks: int, opts: RunOptions, chunk_id_base: int = 0, taps=None):
         """All inputs already on the device.  Returns (raw int16 [n_chunks*250 cap], raw_offsets int64 [n_reads+1],
@@ -174,11 +179,13 @@ class Engine:
         raw, raw_off, tap_out = self.forward_reads_device(
             bases.to(self.device, non_blocking=True), ro.to(self.device, non_blocking=True),
             co.to(self.device, non_blocking=True), n_reads, n_chunks, opts, chunk_id_base, taps)
+        self.check()
         off = raw_off.cpu().numpy()
         sig = raw[: int(off[-1])].cpu().numpy()
         return [sig[off[i]:off[i + 1]] for i in range(n_reads)], tap_out
 
-    def forward_chunks(self, codes: torch.Tensor, opts: RunOptions, chunk_id_base: int = 0, taps=None):
+    def forward_chunks(self, codes: torch.Tensor, opts: RunOptions, chunk_id_base: int = 0, taps=None,
+                       check: bool = True):
         """codes: int8 [C,16,k] on the device (argmax of the one-hot, -1 = zero row) -> pA float32 [C,250]."""
         assert codes.dtype == torch.int8 and codes.is_cuda and codes.is_contiguous()
         n_chunks = codes.shape[0]
@@ -191,6 +198,8 @@ class Engine:
         _lib.check(self.lib.s2s_forward_chunks(self.handle, codes.data_ptr(), n_chunks, C.byref(o), ws.data_ptr(),
                                                ws.numel(), pa.data_ptr(), C.byref(taps_c) if taps_c else None, st),
                    "s2s_forward_chunks")
+        if check:
+            self.check()
         return pa, tap_out
 
     # ---- stage entry points ------------------------------------------------------------------
