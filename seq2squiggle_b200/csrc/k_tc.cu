@@ -73,214 +73,206 @@ __device__ __forceinline__ void layernorm_store(float (&v)[64], const float* s_g
 }
 
 // =================================================================================================
-// G1: QKV projection.  128 threads, 2 CTAs / SM (TMEM 256 columns each).
+// ATT: fused QKV projection + attention for one (chunk, group of 4 heads).  128 threads = 128 rows of a tile,
+// 2 CTAs / SM (TMEM 256 columns and ~109 KB of shared memory each) so one CTA's MMA round trips and row-max
+// pass overlap the other CTA's exponentials.
+//   1. TMA: X16 chunk (2 tiles [128 x 64]) ; the group's weight block [96 x 64] (Wq | Wk | Wv rows) once per CTA
+//   2. UMMA: [128 x 96] = X_tile Wg^T for both tiles (accumulators at TMEM columns 0 and 128)
+//   3. epilogue: + bias, fp16, written straight into the operand layouts in shared memory (never to HBM):
+//        Q  -> bytes [0,64) of the rows of the (now dead) X tiles      (A operand of S, K-slices of 32 B)
+//        K  -> masked 32-byte slots, [256 keys x 128 B]                 (B operand of S)
+//        V  -> transposed and padded, 4 key slabs x [4 heads x 16 rows x 64 keys]   (B operand of P.V)
+//   4. per head and query tile: S MMA (N=256, K=16) -> two-pass softmax on tcgen05.ld double buffers ->
+//      P (fp16) over S in TMEM -> 16 TS MMAs (N=16) -> O / rowsum -> fp16 -> O16 in HBM
 // =================================================================================================
-__global__ void __launch_bounds__(128) k_tc_qkv(const __grid_constant__ CUtensorMap tmX,
-                                                const __grid_constant__ CUtensorMap tmW,
-                                                const float* __restrict__ bias, __half* __restrict__ q16,
-                                                __half* __restrict__ kmask, __half* __restrict__ vt, int n_tiles,
-                                                int* status) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, bar_a[2], bar_mma;
-  __shared__ uint32_t s_tmem;
-  __shared__ int s_abort;
-  __shared__ float s_bias[192];
-  uint8_t* smem = align1024(smem_raw);
-  uint8_t* sW = smem;                 // [192 x 128 B]
-  uint8_t* sA = smem + 192 * 128;     // 2 x [128 x 128 B]
-  const int tid = threadIdx.x, warp = tid >> 5;
-  __shared__ int s_go;
-  if (tid == 0) s_go = (*status == 0);
-  __syncthreads();
-  if (!s_go) return;  // an earlier kernel timed out: unwind quickly (uniform per CTA)
-  if (warp == 0) tmem_alloc<256>(&s_tmem);
-  if (tid == 0) {
-    mbar_init(&bar_w, 1); mbar_init(&bar_a[0], 1); mbar_init(&bar_a[1], 1); mbar_init(&bar_mma, 1);
-    fence_mbar_init();
-    s_abort = 0;
-    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW);
-  }
-  for (int i = tid; i < 192; i += 128) s_bias[i] = bias[i];
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem = s_tmem;
-  int tile = blockIdx.x;
-  if (tid == 0) {
-    mbar_arrive_expect_tx(&bar_w, 192 * 128);
-    tma_load_2d(sW, &tmW, &bar_w, 0, 0);
-    if (tile < n_tiles) {
-      mbar_arrive_expect_tx(&bar_a[0], kSlab);
-      tma_load_2d(sA, &tmX, &bar_a[0], 0, tile * 128);
-    }
-  }
-  wait_bar(&bar_w, 0, status, &s_abort, kErrQkvLoad);
-  const uint32_t idesc = umma_idesc(128, 192, kFmtF16);
-  for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
-    const int next = tile + gridDim.x;
-    if (tid == 0 && next < n_tiles) {  // prefetch the next A tile into the other buffer (its MMA finished last iteration)
-      mbar_arrive_expect_tx(&bar_a[buf ^ 1], kSlab);
-      tma_load_2d(sA + (buf ^ 1) * kSlab, &tmX, &bar_a[buf ^ 1], 0, next * 128);
-    }
-    wait_bar(&bar_a[buf], (it >> 1) & 1, status, &s_abort, kErrQkvLoad);
-    tcgen05_fence_after();
-    if (tid == 0) {
-      const uint32_t a0 = smem_u32(sA + buf * kSlab), b0 = smem_u32(sW);
-#pragma unroll
-      for (int s = 0; s < 4; ++s)
-        umma_f16_ss(tmem, umma_desc_k_sw128(a0 + s * 32), umma_desc_k_sw128(b0 + s * 32), idesc, s > 0);
-      umma_commit(&bar_mma);
-    }
-    wait_bar(&bar_mma, it & 1, status, &s_abort, kErrQkvMma);
-    tcgen05_fence_after();
-    const int64_t row = (int64_t)tile * 128 + tid;
-    const int64_t chunk = tile >> 1;
-    const int t = (tile & 1) * 128 + tid;  // key index inside the chunk
-    const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
-    uint32_t r[32];
-    // ---- Q: columns 0..63 -> fp16 row-major
-#pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-      tmem_ld_32x32(lane_addr + c0, r);
-      tmem_wait_ld();
-      uint32_t pk[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        pk[i] = pack_half2(__uint_as_float(r[2 * i]) + s_bias[c0 + 2 * i], __uint_as_float(r[2 * i + 1]) + s_bias[c0 + 2 * i + 1]);
-      uint4* dst = reinterpret_cast<uint4*>(q16 + row * 64 + c0);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-    }
-    // ---- K: columns 64..127 -> masked 32-byte slot per head: [data|0] for even heads, [0|data] for odd heads
-#pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-      tmem_ld_32x32(lane_addr + 64 + c0, r);
-      tmem_wait_ld();
-      uint4* dst = reinterpret_cast<uint4*>(kmask + row * 128 + c0 * 2);  // head h slot at element offset 16h
-#pragma unroll
-      for (int hh = 0; hh < 4; ++hh) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          pk[i] = pack_half2(__uint_as_float(r[8 * hh + 2 * i]) + s_bias[64 + c0 + 8 * hh + 2 * i],
-                             __uint_as_float(r[8 * hh + 2 * i + 1]) + s_bias[64 + c0 + 8 * hh + 2 * i + 1]);
-        const uint4 data = make_uint4(pk[0], pk[1], pk[2], pk[3]), zero = make_uint4(0u, 0u, 0u, 0u);
-        dst[2 * hh] = (hh & 1) ? zero : data;
-        dst[2 * hh + 1] = (hh & 1) ? data : zero;
-      }
-    }
-    // ---- V: columns 128..191 -> transposed, padded to 16 rows per head (row 8 = ones, rows 9..15 = 0)
-#pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-      tmem_ld_32x32(lane_addr + 128 + c0, r);
-      tmem_wait_ld();
-#pragma unroll
-      for (int hh = 0; hh < 4; ++hh) {
-        const int h = (c0 >> 3) + hh;
-        __half* base = vt + ((chunk * 8 + h) * 16) * 256 + t;
-#pragma unroll
-        for (int d = 0; d < 8; ++d)
-          base[d * 256] = __float2half_rn(__uint_as_float(r[8 * hh + d]) + s_bias[128 + c0 + 8 * hh + d]);
-        base[8 * 256] = __float2half_rn(1.0f);
-#pragma unroll
-        for (int d = 9; d < 16; ++d) base[d * 256] = __float2half_rn(0.0f);
-      }
-    }
-    tcgen05_fence_before();
-    __syncthreads();  // every thread has drained its TMEM reads before the next MMA overwrites the accumulator
-    tcgen05_fence_after();
-  }
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tmem);
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
 }
 
-// =================================================================================================
-// ATT: attention core for one (chunk, group of 4 heads).  128 threads = 128 query rows of a tile.
-// =================================================================================================
-__global__ void __launch_bounds__(128) k_tc_attention(const __grid_constant__ CUtensorMap tmQ,
-                                                      const __grid_constant__ CUtensorMap tmK,
-                                                      const __grid_constant__ CUtensorMap tmV,
-                                                      __half* __restrict__ o16, int n_units, int* status) {
+template <int kValid>
+__device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], float m) {
+  static_assert(kValid % 2 == 0, "pairs");
+#pragma unroll
+  for (int i = 0; i < kValid; i += 2) m = max3(m, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+  return m;
+}
+
+template <int kValid>
+__device__ __forceinline__ void chunk_exp_store(const uint32_t (&r)[32], float scale, float mneg, uint32_t taddr) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float p0 = 2 * i < kValid ? ex2_approx(fmaf(__uint_as_float(r[2 * i]), scale, mneg)) : 0.f;
+    float p1 = 2 * i + 1 < kValid ? ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), scale, mneg)) : 0.f;
+    pk[i] = pack_half2(p0, p1);
+  }
+  tmem_st_32x16(taddr, pk);
+}
+
+__global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUtensorMap tmX,
+                                                    const __grid_constant__ CUtensorMap tmWg,
+                                                    const float* __restrict__ bias_g, __half* __restrict__ o16,
+                                                    int n_units, int* status) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_load, bar_s, bar_o;
+  __shared__ __align__(8) uint64_t bar_load, bar_w, bar_s, bar_o;
   __shared__ uint32_t s_tmem;
-  __shared__ int s_abort;
+  __shared__ int s_abort, s_go;
+  __shared__ float s_bias[2][96];
   uint8_t* smem = align1024(smem_raw);
-  uint8_t* sQ = smem;                  // 2 x [128 x 128 B]   (all 8 heads of both query tiles)
-  uint8_t* sK = smem + 2 * kSlab;      // [256 keys x 128 B]  (masked K of this head group)
+  uint8_t* sXQ = smem;                 // 2 x [128 x 128 B]: X tiles, then Q (bytes [0,64) of each row)
+  uint8_t* sK = smem + 2 * kSlab;      // [256 keys x 128 B]  masked K of this head group
   uint8_t* sV = smem + 4 * kSlab;      // 4 key slabs x [64 rows (4 heads x 16) x 128 B]
+  uint8_t* sW = smem + 6 * kSlab;      // 2 groups... one group at a time: [96 x 128 B]
   const int tid = threadIdx.x, warp = tid >> 5;
-  __shared__ int s_go;
   if (tid == 0) s_go = (*status == 0);
   __syncthreads();
-  if (!s_go) return;  // an earlier kernel timed out: unwind quickly (uniform per CTA)
+  if (!s_go) return;
   if (warp == 0) tmem_alloc<256>(&s_tmem);
   if (tid == 0) {
-    mbar_init(&bar_load, 1); mbar_init(&bar_s, 1); mbar_init(&bar_o, 1);
+    mbar_init(&bar_load, 1); mbar_init(&bar_w, 1); mbar_init(&bar_s, 1); mbar_init(&bar_o, 1);
     fence_mbar_init();
     s_abort = 0;
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmWg);
+  }
+  for (int i = tid; i < 192; i += 128) s_bias[i / 96][i % 96] = bias_g[i];
+  // V^T padding rows are constant: row 8 of every head = ones (softmax denominator), rows 9..15 = 0
+  for (int i = tid; i < 2 * kSlab / 16; i += 128) reinterpret_cast<uint4*>(sV)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  for (int i = tid; i < 4 * 4 * 8; i += 128) {  // (slab, head, 16-byte chunk of 8 keys)
+    const int slab = i >> 5, hh = (i >> 3) & 3, ck = i & 7;
+    const uint32_t one2 = 0x3C003C00u;  // two fp16 ones
+    *reinterpret_cast<uint4*>(sV + slab * 8192 + sw128_offset(hh * 16 + 8, ck)) = make_uint4(one2, one2, one2, one2);
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = s_tmem;
   const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
-  const uint32_t idesc_s = umma_idesc(128, 256, kFmtF16), idesc_o = umma_idesc(128, 16, kFmtF16);
+  const uint32_t idesc_qkv = umma_idesc(128, 96, kFmtF16), idesc_s = umma_idesc(128, 256, kFmtF16),
+                 idesc_o = umma_idesc(128, 16, kFmtF16);
   const float kScale = 0.35355339059327373f * 1.4426950408889634f;  // log2(e) / sqrt(d_k)
-  uint32_t ph_load = 0, ph_s = 0, ph_o = 0;
+  uint32_t ph_load = 0, ph_w = 0, ph_s = 0, ph_o = 0;
+  int cur_g = -1;
   for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
     const int chunk = unit >> 1, g = unit & 1;
     if (tid == 0) {
-      mbar_arrive_expect_tx(&bar_load, 6 * kSlab);
-      tma_load_2d(sQ, &tmQ, &bar_load, 0, chunk * 256);
-      tma_load_2d(sQ + kSlab, &tmQ, &bar_load, 0, chunk * 256 + 128);
-      tma_load_2d(sK, &tmK, &bar_load, g * 64, chunk * 256);
-#pragma unroll
-      for (int s = 0; s < 4; ++s) tma_load_2d(sV + s * 8192, &tmV, &bar_load, s * 64, (chunk * 8 + g * 4) * 16);
+      if (g != cur_g) {  // with an even grid stride every CTA keeps its head group: loaded once
+        mbar_arrive_expect_tx(&bar_w, 96 * 128);
+        tma_load_2d(sW, &tmWg, &bar_w, 0, g * 96);
+      }
+      mbar_arrive_expect_tx(&bar_load, 2 * kSlab);
+      tma_load_2d(sXQ, &tmX, &bar_load, 0, chunk * 256);
+      tma_load_2d(sXQ + kSlab, &tmX, &bar_load, 0, chunk * 256 + 128);
+    }
+    if (g != cur_g) {
+      wait_bar(&bar_w, ph_w, status, &s_abort, kErrAttLoad);
+      ph_w ^= 1;
+      cur_g = g;
     }
     wait_bar(&bar_load, ph_load, status, &s_abort, kErrAttLoad);
     ph_load ^= 1;
     tcgen05_fence_after();
+    if (tid == 0) {  // [128 x 96] = X_tile Wg^T, both tiles
+      const uint32_t w0 = smem_u32(sW);
+#pragma unroll
+      for (int tile = 0; tile < 2; ++tile) {
+        const uint32_t a0 = smem_u32(sXQ + tile * kSlab);
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          umma_f16_ss(tmem + tile * 128, umma_desc_k_sw128(a0 + s * 32), umma_desc_k_sw128(w0 + s * 32), idesc_qkv, s > 0);
+      }
+      umma_commit(&bar_s);
+    }
+    wait_bar(&bar_s, ph_s, status, &s_abort, kErrAttS);
+    ph_s ^= 1;
+    tcgen05_fence_after();
+    {  // QKV epilogue: accumulators -> fp16 operands in shared memory
+      uint32_t r[32];
+      const float* bq = s_bias[g];
+#pragma unroll
+      for (int tile = 0; tile < 2; ++tile) {
+        const int t = tile * 128 + tid;  // key / query index inside the chunk
+        tmem_ld_32x32(lane_addr + tile * 128, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            pk[i] = pack_half2(__uint_as_float(r[8 * hh + 2 * i]) + bq[8 * hh + 2 * i],
+                               __uint_as_float(r[8 * hh + 2 * i + 1]) + bq[8 * hh + 2 * i + 1]);
+          *reinterpret_cast<uint4*>(sXQ + tile * kSlab + sw128_offset(tid, hh)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        tmem_ld_32x32(lane_addr + tile * 128 + 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            pk[i] = pack_half2(__uint_as_float(r[8 * hh + 2 * i]) + bq[32 + 8 * hh + 2 * i],
+                               __uint_as_float(r[8 * hh + 2 * i + 1]) + bq[32 + 8 * hh + 2 * i + 1]);
+          const uint4 data = make_uint4(pk[0], pk[1], pk[2], pk[3]), zero = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(sK + sw128_offset(t, 2 * hh)) = (hh & 1) ? zero : data;
+          *reinterpret_cast<uint4*>(sK + sw128_offset(t, 2 * hh + 1)) = (hh & 1) ? data : zero;
+        }
+        tmem_ld_32x32(lane_addr + tile * 128 + 64, r);
+        tmem_wait_ld();
+        uint8_t* vslab = sV + (t >> 6) * 8192 + (t & 7) * 2;
+        const uint32_t ck = (t & 63) >> 3;
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh)
+#pragma unroll
+          for (int d = 0; d < 8; ++d)
+            *reinterpret_cast<__half*>(vslab + sw128_offset(hh * 16 + d, ck)) =
+                __float2half_rn(__uint_as_float(r[8 * hh + d]) + bq[64 + 8 * hh + d]);
+      }
+    }
+    fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+#pragma unroll 1
     for (int hh = 0; hh < 4; ++hh) {
-      const int h = g * 4 + hh;
+#pragma unroll 1
       for (int tile = 0; tile < 2; ++tile) {
         if (tid == 0) {  // S = Q_h K_h^T : one MMA, N = 256 keys, K = 16 (8 real + 8 masked)
-          umma_f16_ss(tmem, umma_desc_k_sw128(smem_u32(sQ + tile * kSlab) + (h >> 1) * 32),
+          umma_f16_ss(tmem, umma_desc_k_sw128(smem_u32(sXQ + tile * kSlab) + (hh >> 1) * 32),
                       umma_desc_k_sw128(smem_u32(sK) + hh * 32), idesc_s, 0);
           umma_commit(&bar_s);
         }
         wait_bar(&bar_s, ph_s, status, &s_abort, kErrAttS);
         ph_s ^= 1;
         tcgen05_fence_after();
-        uint32_t r[32];
-        // pass 1: row maximum over the 250 real keys
+        uint32_t ra[32], rb[32];
+        // pass 1: row maximum over the 250 real keys (loads double-buffered against the max3 chains)
         float m = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          tmem_ld_32x32(lane_addr + c * 32, r);
-          tmem_wait_ld();
+        tmem_ld_32x32(lane_addr, ra);
+        tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c < 7 || i < S2S_L_DEC - 224) m = fmaxf(m, __uint_as_float(r[i]));
+        for (int c = 0; c < 8; c += 2) {
+          tmem_ld_32x32(lane_addr + (c + 1) * 32, rb);
+          m = chunk_max<32>(ra, m);
+          tmem_wait_ld();
+          if (c + 2 < 8) tmem_ld_32x32(lane_addr + (c + 2) * 32, ra);
+          m = (c + 1 == 7) ? chunk_max<S2S_L_DEC - 224>(rb, m) : chunk_max<32>(rb, m);
+          if (c + 2 < 8) tmem_wait_ld();
         }
         const float mneg = -m * kScale;
-        // pass 2: P = exp2(S*c - m*c) rounded to fp16, written over S (chunk c -> columns [16c,16c+16))
-#pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
-          tmem_ld_32x32(lane_addr + c * 32, r);
-          tmem_wait_ld();
-          uint32_t pk[16];
+        // pass 2: P = exp2(S*c - m*c) -> fp16, written over S (chunk c -> columns [16c,16c+16))
+        tmem_ld_32x32(lane_addr, ra);
+        tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), kScale, mneg));
-            float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), kScale, mneg));
-            if (c == 7 && 2 * i >= S2S_L_DEC - 224) p0 = 0.f;       // keys 250..255 are padding
-            if (c == 7 && 2 * i + 1 >= S2S_L_DEC - 224) p1 = 0.f;
-            pk[i] = pack_half2(p0, p1);
-          }
-          tmem_st_32x16(lane_addr + c * 16, pk);
+        for (int c = 0; c < 8; c += 2) {
+          tmem_ld_32x32(lane_addr + (c + 1) * 32, rb);
+          chunk_exp_store<32>(ra, kScale, mneg, lane_addr + c * 16);
+          tmem_wait_ld();
+          if (c + 2 < 8) tmem_ld_32x32(lane_addr + (c + 2) * 32, ra);
+          if (c + 1 == 7) chunk_exp_store<S2S_L_DEC - 224>(rb, kScale, mneg, lane_addr + (c + 1) * 16);
+          else chunk_exp_store<32>(rb, kScale, mneg, lane_addr + (c + 1) * 16);
+          if (c + 2 < 8) tmem_wait_ld();
         }
         tmem_wait_st();
         tcgen05_fence_before();
@@ -301,7 +293,7 @@ __global__ void __launch_bounds__(128) k_tc_attention(const __grid_constant__ CU
         tmem_wait_ld();
         const float inv = 1.0f / __uint_as_float(o[8]);  // column 8 = sum of the rounded probabilities
         const int64_t row = (int64_t)chunk * 256 + tile * 128 + tid;
-        *reinterpret_cast<uint4*>(o16 + row * 64 + h * 8) =
+        *reinterpret_cast<uint4*>(o16 + row * 64 + (g * 4 + hh) * 8) =
             make_uint4(pack_half2(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv),
                        pack_half2(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv),
                        pack_half2(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv),
@@ -317,214 +309,184 @@ __global__ void __launch_bounds__(128) k_tc_attention(const __grid_constant__ CU
 }
 
 // =================================================================================================
-// G2: Y = LayerNorm(O Wfc^T + b + X).  128 threads, TMEM 64 columns.
+// FFN: X' = LN2(relu(Y W1^T + b1) W2^T + b2 + Y) with Y = LN1(O Wfc^T + b + X), one kernel, 128 rows per
+// tile, 2 CTAs / SM.  TMEM (256 columns): fc accumulator [0,64) ; then D1 [0,256) -> H fp16 packed over
+// [0,128) -> D2 [128,192).  Y (fp32) stays in registers as the second residual; its fp16 copy is written
+// (swizzled) over the consumed O tile in shared memory and is the A operand of W1.
 // =================================================================================================
-__global__ void __launch_bounds__(128) k_tc_fc_ln(const __grid_constant__ CUtensorMap tmA,
-                                                  const __grid_constant__ CUtensorMap tmW,
-                                                  const float* __restrict__ bias, const float* __restrict__ gamma,
-                                                  const float* __restrict__ beta, const float* __restrict__ res,
-                                                  float* __restrict__ y32, __half* __restrict__ y16, int n_tiles,
-                                                  int* status) {
+template <bool kOutHead>
+__global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CUtensorMap tmA,
+                                                      const __grid_constant__ CUtensorMap tmWfc,
+                                                      const __grid_constant__ CUtensorMap tmW1,
+                                                      const __grid_constant__ CUtensorMap tmW2,
+                                                      const float* __restrict__ bfc, const float* __restrict__ g1,
+                                                      const float* __restrict__ be1, const float* __restrict__ b1,
+                                                      const float* __restrict__ b2, const float* __restrict__ g2,
+                                                      const float* __restrict__ be2, float* __restrict__ x32,
+                                                      __half* __restrict__ x16, int n_tiles, int* status) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, bar_a[2], bar_mma;
+  __shared__ __align__(8) uint64_t bar_w, bar_a[2], bar_m0, bar_m1, bar_m2;
   __shared__ uint32_t s_tmem;
-  __shared__ int s_abort;
-  __shared__ float s_bias[64], s_g[64], s_b[64];
+  __shared__ int s_abort, s_go;
+  __shared__ float s_b1[256], s_v[6][64];  // bfc, g1, be1, b2, g2, be2
   uint8_t* smem = align1024(smem_raw);
-  uint8_t* sW = smem;             // [64 x 128 B]
-  uint8_t* sA = smem + 64 * 128;  // 2 x [128 x 128 B]  (8 KB offset keeps 1024-byte alignment)
+  uint8_t* sW1 = smem;                       // [256 x 128 B]
+  uint8_t* sW2 = smem + 2 * kSlab;           // 4 K-slabs x [64 x 128 B]
+  uint8_t* sWfc = smem + 4 * kSlab;          // [64 x 128 B]
+  uint8_t* sA = smem + 4 * kSlab + 8192;     // 2 x [128 x 128 B]: O tile, overwritten by the fp16 Y tile
   const int tid = threadIdx.x, warp = tid >> 5;
-  __shared__ int s_go;
   if (tid == 0) s_go = (*status == 0);
   __syncthreads();
-  if (!s_go) return;  // an earlier kernel timed out: unwind quickly (uniform per CTA)
-  if (warp == 0) tmem_alloc<64>(&s_tmem);
-  if (tid == 0) {
-    mbar_init(&bar_w, 1); mbar_init(&bar_a[0], 1); mbar_init(&bar_a[1], 1); mbar_init(&bar_mma, 1);
-    fence_mbar_init();
-    s_abort = 0;
-    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW);
-  }
-  if (tid < 64) { s_bias[tid] = bias[tid]; s_g[tid] = gamma[tid]; s_b[tid] = beta[tid]; }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem = s_tmem;
-  int tile = blockIdx.x;
-  if (tid == 0) {
-    mbar_arrive_expect_tx(&bar_w, 64 * 128);
-    tma_load_2d(sW, &tmW, &bar_w, 0, 0);
-    if (tile < n_tiles) {
-      mbar_arrive_expect_tx(&bar_a[0], kSlab);
-      tma_load_2d(sA, &tmA, &bar_a[0], 0, tile * 128);
-    }
-  }
-  wait_bar(&bar_w, 0, status, &s_abort, kErrFcLoad);
-  const uint32_t idesc = umma_idesc(128, 64, kFmtF16);
-  for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
-    const int next = tile + gridDim.x;
-    if (tid == 0 && next < n_tiles) {
-      mbar_arrive_expect_tx(&bar_a[buf ^ 1], kSlab);
-      tma_load_2d(sA + (buf ^ 1) * kSlab, &tmA, &bar_a[buf ^ 1], 0, next * 128);
-    }
-    wait_bar(&bar_a[buf], (it >> 1) & 1, status, &s_abort, kErrFcLoad);
-    tcgen05_fence_after();
-    if (tid == 0) {
-      const uint32_t a0 = smem_u32(sA + buf * kSlab), b0 = smem_u32(sW);
-#pragma unroll
-      for (int s = 0; s < 4; ++s)
-        umma_f16_ss(tmem, umma_desc_k_sw128(a0 + s * 32), umma_desc_k_sw128(b0 + s * 32), idesc, s > 0);
-      umma_commit(&bar_mma);
-    }
-    const int64_t row = (int64_t)tile * 128 + tid;
-    float v[64];
-    {  // residual row while the MMA runs
-      const float4* rp = reinterpret_cast<const float4*>(res + row * 64);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float4 x = rp[i];
-        v[4 * i] = x.x + s_bias[4 * i]; v[4 * i + 1] = x.y + s_bias[4 * i + 1];
-        v[4 * i + 2] = x.z + s_bias[4 * i + 2]; v[4 * i + 3] = x.w + s_bias[4 * i + 3];
-      }
-    }
-    wait_bar(&bar_mma, it & 1, status, &s_abort, kErrFcMma);
-    tcgen05_fence_after();
-    const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
-    uint32_t r[32];
-#pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-      tmem_ld_32x32(lane_addr + c0, r);
-      tmem_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[c0 + i] += __uint_as_float(r[i]);
-    }
-    tcgen05_fence_before();
-    layernorm_store(v, s_g, s_b, y32 + row * 64, y16 + row * 64);
-    __syncthreads();
-    tcgen05_fence_after();
-  }
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<64>(tmem);
-}
-
-// =================================================================================================
-// G3: X' = LayerNorm(relu(Y W1^T + b1) W2^T + b2 + Y).  128 threads, 2 CTAs / SM, TMEM 256 columns:
-//     D1 [0,256) fp32 -> H fp16 packed over [0,128) -> D2 [128,192).
-// =================================================================================================
-__global__ void __launch_bounds__(128) k_tc_ffn_ln(const __grid_constant__ CUtensorMap tmA,
-                                                   const __grid_constant__ CUtensorMap tmW1,
-                                                   const __grid_constant__ CUtensorMap tmW2,
-                                                   const float* __restrict__ b1, const float* __restrict__ b2,
-                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                   const float* __restrict__ res, float* __restrict__ x32,
-                                                   __half* __restrict__ x16, int n_tiles, int* status) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, bar_a[2], bar_m1, bar_m2;
-  __shared__ uint32_t s_tmem;
-  __shared__ int s_abort;
-  __shared__ float s_b1[256], s_b2[64], s_g[64], s_b[64];
-  uint8_t* smem = align1024(smem_raw);
-  uint8_t* sW1 = smem;                  // [256 x 128 B]
-  uint8_t* sW2 = smem + 256 * 128;      // 4 K-slabs x [64 x 128 B]
-  uint8_t* sA = smem + 2 * 256 * 128;   // 2 x [128 x 128 B]
-  const int tid = threadIdx.x, warp = tid >> 5;
-  __shared__ int s_go;
-  if (tid == 0) s_go = (*status == 0);
-  __syncthreads();
-  if (!s_go) return;  // an earlier kernel timed out: unwind quickly (uniform per CTA)
+  if (!s_go) return;
   if (warp == 0) tmem_alloc<256>(&s_tmem);
   if (tid == 0) {
-    mbar_init(&bar_w, 1); mbar_init(&bar_a[0], 1); mbar_init(&bar_a[1], 1); mbar_init(&bar_m1, 1); mbar_init(&bar_m2, 1);
+    mbar_init(&bar_w, 1); mbar_init(&bar_a[0], 1); mbar_init(&bar_a[1], 1);
+    mbar_init(&bar_m0, 1); mbar_init(&bar_m1, 1); mbar_init(&bar_m2, 1);
     fence_mbar_init();
     s_abort = 0;
-    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmWfc); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
   }
   for (int i = tid; i < 256; i += 128) s_b1[i] = b1[i];
-  if (tid < 64) { s_b2[tid] = b2[tid]; s_g[tid] = gamma[tid]; s_b[tid] = beta[tid]; }
+  if (tid < 64) {
+    s_v[0][tid] = bfc[tid]; s_v[1][tid] = g1[tid]; s_v[2][tid] = be1[tid];
+    s_v[3][tid] = b2[tid]; s_v[4][tid] = g2[tid]; s_v[5][tid] = be2[tid];
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = s_tmem;
+  const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
   int tile = blockIdx.x;
   if (tid == 0) {
-    mbar_arrive_expect_tx(&bar_w, 2 * 256 * 128);
+    mbar_arrive_expect_tx(&bar_w, 4 * kSlab + 8192);
     tma_load_2d(sW1, &tmW1, &bar_w, 0, 0);
 #pragma unroll
     for (int s = 0; s < 4; ++s) tma_load_2d(sW2 + s * 8192, &tmW2, &bar_w, s * 64, 0);
+    tma_load_2d(sWfc, &tmWfc, &bar_w, 0, 0);
     if (tile < n_tiles) {
       mbar_arrive_expect_tx(&bar_a[0], kSlab);
       tma_load_2d(sA, &tmA, &bar_a[0], 0, tile * 128);
     }
   }
   wait_bar(&bar_w, 0, status, &s_abort, kErrFfnLoad);
-  const uint32_t idesc1 = umma_idesc(128, 256, kFmtF16), idesc2 = umma_idesc(128, 64, kFmtF16);
-  const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
+  const uint32_t idesc64 = umma_idesc(128, 64, kFmtF16), idesc256 = umma_idesc(128, 256, kFmtF16);
   for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
     const int buf = it & 1;
+    const uint32_t ph = it & 1;
+    uint8_t* sAb = sA + buf * kSlab;
     const int next = tile + gridDim.x;
-    if (tid == 0 && next < n_tiles) {
+    if (tid == 0 && next < n_tiles) {  // the other buffer's last reader (W1 MMA of the previous tile) has completed
       mbar_arrive_expect_tx(&bar_a[buf ^ 1], kSlab);
       tma_load_2d(sA + (buf ^ 1) * kSlab, &tmA, &bar_a[buf ^ 1], 0, next * 128);
     }
     wait_bar(&bar_a[buf], (it >> 1) & 1, status, &s_abort, kErrFfnLoad);
     tcgen05_fence_after();
-    if (tid == 0) {
-      const uint32_t a0 = smem_u32(sA + buf * kSlab), b0 = smem_u32(sW1);
+    if (tid == 0) {  // attention output projection
+      const uint32_t a0 = smem_u32(sAb), b0 = smem_u32(sWfc);
 #pragma unroll
       for (int s = 0; s < 4; ++s)
-        umma_f16_ss(tmem, umma_desc_k_sw128(a0 + s * 32), umma_desc_k_sw128(b0 + s * 32), idesc1, s > 0);
-      umma_commit(&bar_m1);
+        umma_f16_ss(tmem, umma_desc_k_sw128(a0 + s * 32), umma_desc_k_sw128(b0 + s * 32), idesc64, s > 0);
+      umma_commit(&bar_m0);
     }
-    wait_bar(&bar_m1, it & 1, status, &s_abort, kErrFfnMma1);
+    const int64_t row = (int64_t)tile * 128 + tid;
+    float y[64];
+    {  // first residual (the block input) while the MMA runs
+      const float4* rp = reinterpret_cast<const float4*>(x32 + row * 64);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float4 x = rp[i];
+        y[4 * i] = x.x + s_v[0][4 * i]; y[4 * i + 1] = x.y + s_v[0][4 * i + 1];
+        y[4 * i + 2] = x.z + s_v[0][4 * i + 2]; y[4 * i + 3] = x.w + s_v[0][4 * i + 3];
+      }
+    }
+    wait_bar(&bar_m0, ph, status, &s_abort, kErrFcMma);
     tcgen05_fence_after();
     uint32_t r[32];
-    // hidden = relu(D1 + b1) -> fp16, packed over the columns already consumed
-#pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
-      tmem_ld_32x32(lane_addr + c * 32, r);
-      tmem_wait_ld();
-      uint32_t pk[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        pk[i] = pack_half2(fmaxf(__uint_as_float(r[2 * i]) + s_b1[c * 32 + 2 * i], 0.f),
-                           fmaxf(__uint_as_float(r[2 * i + 1]) + s_b1[c * 32 + 2 * i + 1], 0.f));
-      tmem_st_32x16(lane_addr + c * 16, pk);
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      tmem_ld_32x32(lane_addr + c0, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) y[c0 + i] += __uint_as_float(r[i]);
+    }
+    {  // LayerNorm 1 (slf_attn.layer_norm); Y stays in registers, fp16 copy -> swizzled A tile over the O tile
+      float mean = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) mean += y[i];
+      mean *= (1.f / 64.f);
+      float var = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) { float d = y[i] - mean; var = fmaf(d, d, var); }
+      const float rstd = 1.0f / sqrtf(var * (1.f / 64.f) + 1e-5f);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) y[i] = (y[i] - mean) * rstd * s_v[1][i] + s_v[2][i];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(sAb + sw128_offset(tid, c)) =
+            make_uint4(pack_half2(y[8 * c], y[8 * c + 1]), pack_half2(y[8 * c + 2], y[8 * c + 3]),
+                       pack_half2(y[8 * c + 4], y[8 * c + 5]), pack_half2(y[8 * c + 6], y[8 * c + 7]));
+    }
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (tid == 0) {  // hidden = Y W1^T
+      tcgen05_fence_after();
+      const uint32_t a0 = smem_u32(sAb), b0 = smem_u32(sW1);
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+        umma_f16_ss(tmem, umma_desc_k_sw128(a0 + s * 32), umma_desc_k_sw128(b0 + s * 32), idesc256, s > 0);
+      umma_commit(&bar_m1);
+    }
+    wait_bar(&bar_m1, ph, status, &s_abort, kErrFfnMma1);
+    tcgen05_fence_after();
+    {  // relu(D1 + b1) -> fp16, packed over the columns already consumed (loads double-buffered)
+      uint32_t rb[32];
+      tmem_ld_32x32(lane_addr, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        tmem_ld_32x32(lane_addr + (c + 1) * 32, rb);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          pk[i] = pack_half2(fmaxf(__uint_as_float(r[2 * i]) + s_b1[c * 32 + 2 * i], 0.f),
+                             fmaxf(__uint_as_float(r[2 * i + 1]) + s_b1[c * 32 + 2 * i + 1], 0.f));
+        tmem_st_32x16(lane_addr + c * 16, pk);
+        tmem_wait_ld();
+        if (c + 2 < 8) tmem_ld_32x32(lane_addr + (c + 2) * 32, r);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          pk[i] = pack_half2(fmaxf(__uint_as_float(rb[2 * i]) + s_b1[(c + 1) * 32 + 2 * i], 0.f),
+                             fmaxf(__uint_as_float(rb[2 * i + 1]) + s_b1[(c + 1) * 32 + 2 * i + 1], 0.f));
+        tmem_st_32x16(lane_addr + (c + 1) * 16, pk);
+        if (c + 2 < 8) tmem_wait_ld();
+      }
     }
     tmem_wait_st();
     tcgen05_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0) {  // D2 = H W2^T, A operand from TMEM
       tcgen05_fence_after();
       const uint32_t w2 = smem_u32(sW2);
 #pragma unroll
       for (int s = 0; s < 16; ++s)
-        umma_f16_ts(tmem + 128, tmem + 8 * s, umma_desc_k_sw128(w2 + (s >> 2) * 8192 + (s & 3) * 32), idesc2, s > 0);
+        umma_f16_ts(tmem + 128, tmem + 8 * s, umma_desc_k_sw128(w2 + (s >> 2) * 8192 + (s & 3) * 32), idesc64, s > 0);
       umma_commit(&bar_m2);
     }
-    const int64_t row = (int64_t)tile * 128 + tid;
-    float v[64];
-    {
-      const float4* rp = reinterpret_cast<const float4*>(res + row * 64);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float4 x = rp[i];
-        v[4 * i] = x.x + s_b2[4 * i]; v[4 * i + 1] = x.y + s_b2[4 * i + 1];
-        v[4 * i + 2] = x.z + s_b2[4 * i + 2]; v[4 * i + 3] = x.w + s_b2[4 * i + 3];
-      }
-    }
-    wait_bar(&bar_m2, it & 1, status, &s_abort, kErrFfnMma2);
+    for (int i = 0; i < 64; ++i) y[i] += s_v[3][i];
+    wait_bar(&bar_m2, ph, status, &s_abort, kErrFfnMma2);
     tcgen05_fence_after();
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 32) {
       tmem_ld_32x32(lane_addr + 128 + c0, r);
       tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[c0 + i] += __uint_as_float(r[i]);
+      for (int i = 0; i < 32; ++i) y[c0 + i] += __uint_as_float(r[i]);
     }
     tcgen05_fence_before();
-    layernorm_store(v, s_g, s_b, x32 + row * 64, x16 + row * 64);
-    __syncthreads();
+    layernorm_store(y, s_v[4], s_v[5], x32 + row * 64, x16 + row * 64);
+    __syncthreads();  // all TMEM reads are done before the next tile's MMA overwrites the accumulators
     tcgen05_fence_after();
   }
   __syncthreads();
@@ -538,10 +500,8 @@ __global__ void k_f32_to_f16(const float* __restrict__ x, __half* __restrict__ y
   }
 }
 
-constexpr int kSmemQkv = 81920;             // 57 KB used; padded so at most 2 CTAs (2 x 256 TMEM columns) share an SM
-constexpr int kSmemAtt = 6 * kSlab + 1024;  // 97 KB -> 2 CTAs / SM
-constexpr int kSmemFc = 64 * 128 + 2 * kSlab + 1024;
-constexpr int kSmemFfn = 6 * kSlab + 1024;
+constexpr int kSmemAtt = 6 * kSlab + 96 * 128 + 1024;   // 109 KB -> 2 CTAs / SM
+constexpr int kSmemFfn = 6 * kSlab + 8192 + 1024;       // 105 KB -> 2 CTAs / SM
 
 }  // namespace
 
@@ -554,12 +514,7 @@ void tc_carve(TcBuffers& b, char* base, int64_t& off, int64_t bc) {
   };
   const int64_t rows = bc * S2S_L_DEC_PAD;
   b.x16 = reinterpret_cast<__half*>(take(rows * 64 * 2));
-  b.q16 = reinterpret_cast<__half*>(take(rows * 64 * 2));
-  b.k16 = reinterpret_cast<__half*>(take(rows * 128 * 2));
-  b.vt16 = reinterpret_cast<__half*>(take(bc * 8 * 16 * 256 * 2));
   b.o16 = reinterpret_cast<__half*>(take(rows * 64 * 2));
-  b.y16 = reinterpret_cast<__half*>(take(rows * 64 * 2));
-  b.y32 = reinterpret_cast<float*>(take(rows * 64 * 4));
 }
 
 int tc_init(TcState& s, const DevWeights& w, int device) {
@@ -572,10 +527,8 @@ int tc_init(TcState& s, const DevWeights& w, int device) {
     set_error("cuTensorMapEncodeTiled driver entry point not found");
     return -1;
   }
-  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_qkv, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemQkv));
-  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt));
-  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFc));
-  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_ffn_ln, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt));
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
   (void)w;
   S2S_CUDA_OK(cudaMalloc(&s.d_status, 256));
   S2S_CUDA_OK(cudaMemset(s.d_status, 0, 256));
@@ -594,13 +547,9 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, 
   const int n_tiles = (int)(rows / 128);
   const CUtensorMapDataType f16 = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
-  CUtensorMap tmX, tmQ, tmK, tmV, tmO, tmY;
+  CUtensorMap tmX, tmO;
   bool ok = make_tmap_2d(enc, &tmX, b.x16, f16, 2, rows, 64, 128, 64, sw) &&
-            make_tmap_2d(enc, &tmQ, b.q16, f16, 2, rows, 64, 128, 64, sw) &&
-            make_tmap_2d(enc, &tmK, b.k16, f16, 2, rows, 128, 256, 64, sw) &&
-            make_tmap_2d(enc, &tmV, b.vt16, f16, 2, (uint64_t)n_chunks * 128, 256, 64, 64, sw) &&
-            make_tmap_2d(enc, &tmO, b.o16, f16, 2, rows, 64, 128, 64, sw) &&
-            make_tmap_2d(enc, &tmY, b.y16, f16, 2, rows, 64, 128, 64, sw);
+            make_tmap_2d(enc, &tmO, b.o16, f16, 2, rows, 64, 128, 64, sw);
   if (!ok) {
     set_error("cuTensorMapEncodeTiled failed for an activation tensor");
     return -1;
@@ -613,13 +562,12 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, 
     S2S_LAUNCH_CHECK();
   }
   const int grid2 = n_tiles < 2 * s.sm_count ? n_tiles : 2 * s.sm_count;
-  const int grid4 = n_tiles < 4 * s.sm_count ? n_tiles : 4 * s.sm_count;
   const int n_units = (int)(2 * n_chunks);
-  const int grid_att = n_units < 2 * s.sm_count ? n_units : 2 * s.sm_count;
+  const int grid_att = n_units < 2 * s.sm_count ? n_units : 2 * s.sm_count;  // even stride: a CTA keeps its head group
   for (int l = 0; l < w.cfg.decoder_layers; ++l) {
     const BlockDev& bl = w.dec[l];
-    CUtensorMap tmWqkv, tmWfc, tmW1, tmW2;
-    ok = make_tmap_2d(enc, &tmWqkv, bl.wqkv_h, f16, 2, 192, 64, 192, 64, sw) &&
+    CUtensorMap tmWg, tmWfc, tmW1, tmW2;
+    ok = make_tmap_2d(enc, &tmWg, bl.wg_h, f16, 2, 192, 64, 96, 64, sw) &&
          make_tmap_2d(enc, &tmWfc, bl.fc_h, f16, 2, 64, 64, 64, 64, sw) &&
          make_tmap_2d(enc, &tmW1, bl.w1_h, f16, 2, 256, 64, 256, 64, sw) &&
          make_tmap_2d(enc, &tmW2, bl.w2_h, f16, 2, 64, 256, 64, 64, sw);
@@ -627,24 +575,20 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, 
       set_error("cuTensorMapEncodeTiled failed for a weight tensor");
       return -1;
     }
-    k_tc_qkv<<<grid2, 128, kSmemQkv, st>>>(tmX, tmWqkv, bl.bqkv, b.q16, b.k16, b.vt16, n_tiles, s.d_status);
-    S2S_LAUNCH_CHECK();
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (s.prof_on) {
       cudaEventCreate(&e0); cudaEventCreate(&e1);
       cudaEventRecord(e0, st);
     }
-    k_tc_attention<<<grid_att, 128, kSmemAtt, st>>>(tmQ, tmK, tmV, b.o16, n_units, s.d_status);
+    k_tc_attn<<<grid_att, 128, kSmemAtt, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, s.d_status);
     S2S_LAUNCH_CHECK();
     if (s.prof_on) {
       cudaEventRecord(e1, st);
       s.prof_events.push_back(e0); s.prof_events.push_back(e1);
       s.prof_chunks += n_chunks;
     }
-    k_tc_fc_ln<<<grid4, 128, kSmemFc, st>>>(tmO, tmWfc, bl.fc_b, bl.ln1_w, bl.ln1_b, x32, b.y32, b.y16, n_tiles, s.d_status);
-    S2S_LAUNCH_CHECK();
-    k_tc_ffn_ln<<<grid2, 128, kSmemFfn, st>>>(tmY, tmW1, tmW2, bl.b1, bl.b2, bl.ln2_w, bl.ln2_b, b.y32, x32, b.x16,
-                                              n_tiles, s.d_status);
+    k_tc_fc_ffn<false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, bl.fc_b, bl.ln1_w, bl.ln1_b, bl.b1, bl.b2,
+                                                     bl.ln2_w, bl.ln2_b, x32, b.x16, n_tiles, s.d_status);
     S2S_LAUNCH_CHECK();
   }
   return 0;

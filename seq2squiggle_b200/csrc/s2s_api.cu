@@ -65,7 +65,7 @@ struct Packer {
 };
 
 struct BlockOff {
-  int64_t wqkv_t, bqkv, fc_t, fc_b, w1_t, b1, w2_t, b2, ln1_w, ln1_b, ln2_w, ln2_b, wqkv_h, fc_h, w1_h, w2_h;
+  int64_t wqkv_t, bqkv, fc_t, fc_b, w1_t, b1, w2_t, b2, ln1_w, ln1_b, ln2_w, ln2_b, wqkv_h, fc_h, w1_h, w2_h, wg_h, bg;
 };
 
 BlockOff pack_block(Packer& pk, const BlockW& b) {
@@ -94,6 +94,15 @@ BlockOff pack_block(Packer& pk, const BlockW& b) {
   o.fc_h = pk.put_h(b.fc_w, 64 * 64);
   o.w1_h = pk.put_h(b.w1, 256 * 64);
   o.w2_h = pk.put_h(b.w2, 64 * 256);
+  // per head group g (4 heads): [96][64] = Wq rows 32g.., Wk rows 32g.., Wv rows 32g..  (+ bias [96])
+  std::vector<float> wg(2 * 96 * 64), bgv(2 * 96);
+  for (int g = 0; g < 2; ++g)
+    for (int part = 0; part < 3; ++part) {
+      memcpy(wg.data() + ((size_t)g * 96 + part * 32) * 64, cat.data() + ((size_t)part * 64 + g * 32) * 64, 32 * 64 * 4);
+      memcpy(bgv.data() + g * 96 + part * 32, bias.data() + part * 64 + g * 32, 32 * 4);
+    }
+  o.wg_h = pk.put_h(wg.data(), 2 * 96 * 64);
+  o.bg = pk.put(bgv.data(), 2 * 96);
   return o;
 }
 
@@ -102,6 +111,7 @@ void bind_block(BlockDev& d, const BlockOff& o, const float* f, const __half* h)
   d.w1_t = f + o.w1_t; d.b1 = f + o.b1; d.w2_t = f + o.w2_t; d.b2 = f + o.b2;
   d.ln1_w = f + o.ln1_w; d.ln1_b = f + o.ln1_b; d.ln2_w = f + o.ln2_w; d.ln2_b = f + o.ln2_b;
   d.wqkv_h = h + o.wqkv_h; d.fc_h = h + o.fc_h; d.w1_h = h + o.w1_h; d.w2_h = h + o.w2_h;
+  d.wg_h = h + o.wg_h; d.bg = f + o.bg;
 }
 
 int check_config(const s2s_config* c) {

@@ -18,6 +18,8 @@ struct BlockDev {
   const __half *fc_h;          // [64][64]
   const __half *w1_h;          // [256][64]
   const __half *w2_h;          // [64][256]
+  const __half *wg_h;          // [2][96][64]: per group of 4 heads, rows = Wq(32) | Wk(32) | Wv(32)
+  const float *bg;             // [2][96]
 };
 
 struct DevWeights {

@@ -20,12 +20,7 @@ struct TcState {
 // Per-sub-batch device buffers of the tensor-core path (carved from the caller's workspace).
 struct TcBuffers {
   __half* x16 = nullptr;    // [rows,64]  fp16 copy of the residual stream (GEMM A operand)
-  __half* q16 = nullptr;    // [rows,64]
-  __half* k16 = nullptr;    // [rows,64]
-  __half* vt16 = nullptr;   // [chunks][64][256] V transposed (K-major B operand of P.V)
   __half* o16 = nullptr;    // [rows,64]  attention output (A operand of fc)
-  __half* y16 = nullptr;    // [rows,64]
-  float* y32 = nullptr;     // [rows,64]
 };
 
 void tc_carve(TcBuffers& b, char* base, int64_t& off, int64_t batch_chunks);
