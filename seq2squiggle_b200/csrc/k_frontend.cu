@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(256) k_embed(const float* __restrict__ src_t, 
                                                const float* __restrict__ enc_pos, int k,
                                                const uint8_t* __restrict__ bases, const int64_t* __restrict__ chunk_base,
                                                const int32_t* __restrict__ chunk_nk, const int8_t* __restrict__ codes,
-                                               int64_t n_chunks, float* __restrict__ emb_out, float* __restrict__ x_enc) {
+                                               int64_t n_chunks, float* __restrict__ emb_out, float* __restrict__ x_enc,
+                                               __half* __restrict__ x_enc16) {
   __shared__ int8_t s_code[S2S_L_ENC][12];
   __shared__ __align__(16) float s_e1[S2S_L_ENC][S2S_D];
   const int64_t c = blockIdx.x;
@@ -91,6 +92,10 @@ __global__ void __launch_bounds__(256) k_embed(const float* __restrict__ src_t, 
   float4 p = *reinterpret_cast<const float4*>(enc_pos + j * S2S_D + 4 * cg);
   o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
   *reinterpret_cast<float4*>(x_enc + off) = o;
+  if (x_enc16) {
+    __half2 a = __floats2half2_rn(o.x, o.y), b = __floats2half2_rn(o.z, o.w);
+    *reinterpret_cast<uint2*>(x_enc16 + off) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+  }
 }
 
 int launch_chunk_map(const int64_t* read_offsets, const int64_t* chunk_offsets, int64_t n_reads, int64_t n_chunks,
@@ -103,10 +108,10 @@ int launch_chunk_map(const int64_t* read_offsets, const int64_t* chunk_offsets, 
 }
 
 int launch_embed(const DevWeights& w, const uint8_t* bases, const int64_t* chunk_base, const int32_t* chunk_nk,
-                 const int8_t* codes, int64_t n_chunks, float* emb_out, float* x_enc, cudaStream_t st) {
+                 const int8_t* codes, int64_t n_chunks, float* emb_out, float* x_enc, __half* x_enc16, cudaStream_t st) {
   if (n_chunks == 0) return 0;
   k_embed<<<(unsigned)n_chunks, 256, 0, st>>>(w.src_t, w.src_b, w.pre_t, w.pre_b, w.enc_pos, w.cfg.seq_kmer, bases,
-                                              chunk_base, chunk_nk, codes, n_chunks, emb_out, x_enc);
+                                              chunk_base, chunk_nk, codes, n_chunks, emb_out, x_enc, x_enc16);
   S2S_LAUNCH_CHECK();
   return 0;
 }

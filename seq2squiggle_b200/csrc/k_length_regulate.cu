@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(256) k_length_regulate(const float* __restrict
                                                          const float* __restrict__ sigma,
                                                          const int32_t* __restrict__ dur,
                                                          const float* __restrict__ dec_pos, float* __restrict__ x_dec,
-                                                         int rows_out, float* __restrict__ sigma_ext,
+                                                         __half* __restrict__ x_dec16, int rows_out, float* __restrict__ sigma_ext,
                                                          int32_t* __restrict__ total, float* __restrict__ lr_tap) {
   __shared__ __align__(16) float s_x[S2S_L_ENC][S2S_D];
   __shared__ float s_sig[S2S_L_ENC];
@@ -57,14 +57,19 @@ __global__ void __launch_bounds__(256) k_length_regulate(const float* __restrict
       }
     }
     if (x_dec) *reinterpret_cast<float4*>(x_dec + ((size_t)c * rows_out + t) * S2S_D + 4 * q) = v;
+    if (x_dec16) {
+      __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+      *reinterpret_cast<uint2*>(x_dec16 + ((size_t)c * rows_out + t) * S2S_D + 4 * q) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    }
   }
 }
 
 int launch_length_regulate(const float* enc_out, const float* sigma, const int32_t* dur, int64_t n_chunks,
-                           const float* dec_pos, float* x_dec, int rows_per_chunk_out, float* sigma_ext,
-                           int32_t* total, float* lr_tap, cudaStream_t st) {
+                           const float* dec_pos, float* x_dec, __half* x_dec16, int rows_per_chunk_out,
+                           float* sigma_ext, int32_t* total, float* lr_tap, cudaStream_t st) {
   if (n_chunks == 0) return 0;
-  k_length_regulate<<<(unsigned)n_chunks, 256, 0, st>>>(enc_out, sigma, dur, dec_pos, x_dec, rows_per_chunk_out,
+  k_length_regulate<<<(unsigned)n_chunks, 256, 0, st>>>(enc_out, sigma, dur, dec_pos, x_dec, x_dec16, rows_per_chunk_out,
                                                         sigma_ext, total, lr_tap);
   S2S_LAUNCH_CHECK();
   return 0;

@@ -178,7 +178,8 @@ __global__ void __launch_bounds__(256) k_attention_dec_f32(const float* __restri
 }
 
 // Encoder length (16 keys): one CTA of 128 threads per chunk, thread = (head, query).
-__global__ void __launch_bounds__(128) k_attention_enc_f32(const float* __restrict__ qkv, float* __restrict__ out) {
+template <typename OutT>
+__global__ void __launch_bounds__(128) k_attention_enc_f32(const float* __restrict__ qkv, OutT* __restrict__ out) {
   __shared__ __align__(16) float s[S2S_L_ENC][192];
   const int64_t c = blockIdx.x;
   const int tid = threadIdx.x;
@@ -208,21 +209,35 @@ __global__ void __launch_bounds__(128) k_attention_enc_f32(const float* __restri
     for (int d = 0; d < 8; ++d) o[d] = fmaf(p, s[j][128 + 8 * h + d], o[d]);
   }
   const float inv = 1.0f / sum;
-  float* op = out + (c * S2S_L_ENC + qi) * 64 + 8 * h;
-  *reinterpret_cast<float4*>(op) = make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
-  *reinterpret_cast<float4*>(op + 4) = make_float4(o[4] * inv, o[5] * inv, o[6] * inv, o[7] * inv);
+  OutT* op = out + (c * S2S_L_ENC + qi) * 64 + 8 * h;
+  if constexpr (sizeof(OutT) == 4) {
+    *reinterpret_cast<float4*>(op) = make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
+    *reinterpret_cast<float4*>(op + 4) = make_float4(o[4] * inv, o[5] * inv, o[6] * inv, o[7] * inv);
+  } else {
+    __half2 h0 = __floats2half2_rn(o[0] * inv, o[1] * inv), h1 = __floats2half2_rn(o[2] * inv, o[3] * inv);
+    __half2 h2 = __floats2half2_rn(o[4] * inv, o[5] * inv), h3 = __floats2half2_rn(o[6] * inv, o[7] * inv);
+    *reinterpret_cast<uint4*>(op) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+  }
 }
 
 int launch_attention_f32(const float* qkv, float* out, int64_t n_chunks, int L, int rows_per_chunk, cudaStream_t st) {
   if (n_chunks == 0) return 0;
   if (L == S2S_L_ENC && rows_per_chunk == S2S_L_ENC) {
-    k_attention_enc_f32<<<(unsigned)n_chunks, 128, 0, st>>>(qkv, out);
+    k_attention_enc_f32<float><<<(unsigned)n_chunks, 128, 0, st>>>(qkv, out);
   } else if (L == S2S_L_DEC && rows_per_chunk == S2S_L_DEC_PAD) {
     k_attention_dec_f32<<<(unsigned)(n_chunks * 8), 256, 0, st>>>(qkv, out);
   } else {
     set_error("launch_attention_f32: unsupported L=%d rows_per_chunk=%d", L, rows_per_chunk);
     return -1;
   }
+  S2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_attention_enc_f16out(const float* qkv, __half* out, int64_t n_chunks, cudaStream_t st) {
+  if (n_chunks == 0) return 0;
+  k_attention_enc_f32<__half><<<(unsigned)n_chunks, 128, 0, st>>>(qkv, out);
   S2S_LAUNCH_CHECK();
   return 0;
 }

@@ -493,6 +493,91 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
   if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
+// =================================================================================================
+// ENC-QKV: qkv[rows,192] (fp32) = X Wqkv^T + b for the encoder rows (16 per chunk; the 16-key attention itself
+// runs on CUDA cores).  128 threads, TMEM 256 columns, 2 CTAs / SM.
+// =================================================================================================
+__global__ void __launch_bounds__(128, 2) k_tc_qkv_plain(const __grid_constant__ CUtensorMap tmX,
+                                                         const __grid_constant__ CUtensorMap tmW,
+                                                         const float* __restrict__ bias, float* __restrict__ qkv,
+                                                         int64_t n_rows, int* status) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_w, bar_a[2], bar_mma;
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_abort, s_go;
+  __shared__ float s_bias[192];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sW = smem;                 // [192 x 128 B]
+  uint8_t* sA = smem + 192 * 128;     // 2 x [128 x 128 B]
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_tiles = (int)((n_rows + 127) / 128);
+  if (tid == 0) s_go = (*status == 0);
+  __syncthreads();
+  if (!s_go) return;
+  if (warp == 0) tmem_alloc<256>(&s_tmem);
+  if (tid == 0) {
+    mbar_init(&bar_w, 1); mbar_init(&bar_a[0], 1); mbar_init(&bar_a[1], 1); mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+    s_abort = 0;
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW);
+  }
+  for (int i = tid; i < 192; i += 128) s_bias[i] = bias[i];
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s_tmem;
+  int tile = blockIdx.x;
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar_w, 192 * 128);
+    tma_load_2d(sW, &tmW, &bar_w, 0, 0);
+    if (tile < n_tiles) {
+      mbar_arrive_expect_tx(&bar_a[0], kSlab);
+      tma_load_2d(sA, &tmX, &bar_a[0], 0, tile * 128);   // rows past n_rows are zero-filled by TMA
+    }
+  }
+  wait_bar(&bar_w, 0, status, &s_abort, kErrQkvLoad);
+  const uint32_t idesc = umma_idesc(128, 192, kFmtF16);
+  for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int next = tile + gridDim.x;
+    if (tid == 0 && next < n_tiles) {
+      mbar_arrive_expect_tx(&bar_a[buf ^ 1], kSlab);
+      tma_load_2d(sA + (buf ^ 1) * kSlab, &tmX, &bar_a[buf ^ 1], 0, next * 128);
+    }
+    wait_bar(&bar_a[buf], (it >> 1) & 1, status, &s_abort, kErrQkvLoad);
+    tcgen05_fence_after();
+    if (tid == 0) {
+      const uint32_t a0 = smem_u32(sA + buf * kSlab), b0 = smem_u32(sW);
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+        umma_f16_ss(tmem, umma_desc_k_sw128(a0 + s * 32), umma_desc_k_sw128(b0 + s * 32), idesc, s > 0);
+      umma_commit(&bar_mma);
+    }
+    wait_bar(&bar_mma, it & 1, status, &s_abort, kErrQkvMma);
+    tcgen05_fence_after();
+    const int64_t row = (int64_t)tile * 128 + tid;
+    const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
+    uint32_t r[32];
+#pragma unroll
+    for (int c0 = 0; c0 < 192; c0 += 32) {
+      tmem_ld_32x32(lane_addr + c0, r);
+      tmem_wait_ld();
+      if (row < n_rows) {
+        float4* dst = reinterpret_cast<float4*>(qkv + row * 192 + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          dst[i] = make_float4(__uint_as_float(r[4 * i]) + s_bias[c0 + 4 * i], __uint_as_float(r[4 * i + 1]) + s_bias[c0 + 4 * i + 1],
+                               __uint_as_float(r[4 * i + 2]) + s_bias[c0 + 4 * i + 2], __uint_as_float(r[4 * i + 3]) + s_bias[c0 + 4 * i + 3]);
+      }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
 __global__ void k_f32_to_f16(const float* __restrict__ x, __half* __restrict__ y, int64_t n4) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -500,6 +585,7 @@ __global__ void k_f32_to_f16(const float* __restrict__ x, __half* __restrict__ y
   }
 }
 
+constexpr int kSmemQkv = 81920;                          // 57 KB used; padded so <= 2 CTAs (TMEM 2 x 256) per SM
 constexpr int kSmemAtt = 6 * kSlab + 96 * 128 + 1024;   // 109 KB -> 2 CTAs / SM
 constexpr int kSmemFfn = 6 * kSlab + 8192 + 1024;       // 105 KB -> 2 CTAs / SM
 
@@ -515,6 +601,9 @@ void tc_carve(TcBuffers& b, char* base, int64_t& off, int64_t bc) {
   const int64_t rows = bc * S2S_L_DEC_PAD;
   b.x16 = reinterpret_cast<__half*>(take(rows * 64 * 2));
   b.o16 = reinterpret_cast<__half*>(take(rows * 64 * 2));
+  const int64_t erows = align_up(bc * S2S_L_ENC, 128);
+  b.xe16 = reinterpret_cast<__half*>(take(erows * 64 * 2));
+  b.oe16 = reinterpret_cast<__half*>(take(erows * 64 * 2));
 }
 
 int tc_init(TcState& s, const DevWeights& w, int device) {
@@ -527,6 +616,7 @@ int tc_init(TcState& s, const DevWeights& w, int device) {
     set_error("cuTensorMapEncodeTiled driver entry point not found");
     return -1;
   }
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_qkv_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemQkv));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
   (void)w;
@@ -553,13 +643,6 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, 
   if (!ok) {
     set_error("cuTensorMapEncodeTiled failed for an activation tensor");
     return -1;
-  }
-  {  // fp16 copy of the decoder input (the fp32 residual stream stays the master copy)
-    const int64_t n4 = (int64_t)rows * 16;
-    int64_t blocks = ceil_div(n4, 256);
-    if (blocks > s.sm_count * 16) blocks = s.sm_count * 16;
-    k_f32_to_f16<<<(unsigned)blocks, 256, 0, st>>>(x32, b.x16, n4);
-    S2S_LAUNCH_CHECK();
   }
   const int grid2 = n_tiles < 2 * s.sm_count ? n_tiles : 2 * s.sm_count;
   const int n_units = (int)(2 * n_chunks);
@@ -591,6 +674,47 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, 
                                                      bl.ln2_w, bl.ln2_b, x32, b.x16, n_tiles, s.d_status);
     S2S_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+
+// Encoder FFT blocks (modules.py:82-87) on the tensor cores: rows = 16 per chunk.  x32/x16 in place.
+int tc_encoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, __half* x16, float* qkv32, __half* o16,
+               int64_t n_chunks, cudaStream_t st) {
+  if (n_chunks == 0) return 0;
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(s.encode_tiled);
+  const uint64_t rows = (uint64_t)n_chunks * S2S_L_ENC;
+  const int n_tiles = (int)((rows + 127) / 128);
+  const CUtensorMapDataType f16 = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  CUtensorMap tmX, tmO;
+  // the buffers are padded to whole 128-row tiles by the workspace carver
+  bool ok = make_tmap_2d(enc, &tmX, x16, f16, 2, (uint64_t)n_tiles * 128, 64, 128, 64, sw) &&
+            make_tmap_2d(enc, &tmO, o16, f16, 2, (uint64_t)n_tiles * 128, 64, 128, 64, sw);
+  if (!ok) {
+    set_error("cuTensorMapEncodeTiled failed for an encoder activation tensor");
+    return -1;
+  }
+  const int grid2 = n_tiles < 2 * s.sm_count ? n_tiles : 2 * s.sm_count;
+  for (int l = 0; l < w.cfg.encoder_layers; ++l) {
+    const BlockDev& bl = w.enc[l];
+    CUtensorMap tmWqkv, tmWfc, tmW1, tmW2;
+    ok = make_tmap_2d(enc, &tmWqkv, bl.wqkv_h, f16, 2, 192, 64, 192, 64, sw) &&
+         make_tmap_2d(enc, &tmWfc, bl.fc_h, f16, 2, 64, 64, 64, 64, sw) &&
+         make_tmap_2d(enc, &tmW1, bl.w1_h, f16, 2, 256, 64, 256, 64, sw) &&
+         make_tmap_2d(enc, &tmW2, bl.w2_h, f16, 2, 64, 256, 64, 64, sw);
+    if (!ok) {
+      set_error("cuTensorMapEncodeTiled failed for a weight tensor");
+      return -1;
+    }
+    k_tc_qkv_plain<<<grid2, 128, kSmemQkv, st>>>(tmX, tmWqkv, bl.bqkv, qkv32, (int64_t)rows, s.d_status);
+    S2S_LAUNCH_CHECK();
+    if (launch_attention_enc_f16out(qkv32, o16, n_chunks, st)) return -1;
+    k_tc_fc_ffn<false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, bl.fc_b, bl.ln1_w, bl.ln1_b, bl.b1, bl.b2,
+                                                     bl.ln2_w, bl.ln2_b, x32, x16, n_tiles, s.d_status);
+    S2S_LAUNCH_CHECK();
+  }
+  (void)b;
   return 0;
 }
 

@@ -170,8 +170,8 @@ int64_t carve(Workspace& w, void* base, const s2s_engine* h, int64_t n_chunks, i
   w.compact_bytes = compact_workspace_bytes(n_chunks);
   w.compact_ws = cv.take<char>(w.compact_bytes);
   w.emb = cv.take<float>(me * 64);
-  w.xe = cv.take<float>(me * 64);
-  w.qkv_e = cv.take<float>(me * 192);
+  w.xe = cv.take<float>(align_up(me, 128) * 64);   // whole 128-row tiles for the tensor-core encoder
+  w.qkv_e = cv.take<float>(align_up(me, 128) * 192);
   w.att_e = cv.take<float>(me * 64);
   w.ye = cv.take<float>(me * 64);
   w.he = cv.take<float>(me * 256);
@@ -212,6 +212,7 @@ int run_pipeline(s2s_engine* h, const uint8_t* bases, const int8_t* codes, const
                  const s2s_run_opts& opts, float* pa_out, const s2s_taps* taps, cudaStream_t st) {
   const DevWeights& dw = h->dw;
   const int k = h->cfg.seq_kmer;
+  const bool tc_path = opts.precision == S2S_PREC_FP16_TC;
   for (int64_t c0 = 0; c0 < n_chunks; c0 += h->batch_chunks) {
     const int64_t bc = (n_chunks - c0) < h->batch_chunks ? (n_chunks - c0) : h->batch_chunks;
     const int64_t me = bc * S2S_L_ENC;
@@ -219,10 +220,15 @@ int run_pipeline(s2s_engine* h, const uint8_t* bases, const int8_t* codes, const
     o.chunk_id_base = opts.chunk_id_base + (uint64_t)c0;
     // K-A
     if (launch_embed(dw, bases, bases ? w.chunk_base + c0 : nullptr, bases ? w.chunk_nk + c0 : nullptr,
-                     codes ? codes + c0 * S2S_L_ENC * k : nullptr, bc, w.emb, w.xe, st)) return -1;
+                     codes ? codes + c0 * S2S_L_ENC * k : nullptr, bc, w.emb, w.xe, tc_path ? w.tcb.xe16 : nullptr, st))
+      return -1;
     // encoder (modules.py:82-87)
-    for (int l = 0; l < h->cfg.encoder_layers; ++l)
-      if (fft_block_f32(dw.enc[l], w.xe, w.ye, w.qkv_e, w.att_e, w.he, bc, S2S_L_ENC, S2S_L_ENC, st)) return -1;
+    if (tc_path) {
+      if (tc_encoder(h->tc, dw, w.tcb, w.xe, w.tcb.xe16, w.qkv_e, w.tcb.oe16, bc, st)) return -1;
+    } else {
+      for (int l = 0; l < h->cfg.encoder_layers; ++l)
+        if (fft_block_f32(dw.enc[l], w.xe, w.ye, w.qkv_e, w.att_e, w.he, bc, S2S_L_ENC, S2S_L_ENC, st)) return -1;
+    }
     // samplers (K-C)
     if (launch_linear_f32(w.emb, dw.smp0_t, dw.smp0_b, nullptr, nullptr, nullptr, w.h3, me, 64, 192, EPI_BIAS_RELU, st))
       return -1;
@@ -230,7 +236,8 @@ int run_pipeline(s2s_engine* h, const uint8_t* bases, const int8_t* codes, const
                              taps && taps->rate_dev ? taps->rate_dev + c0 * 16 : nullptr,
                              taps && taps->dur_float_dev ? taps->dur_float_dev + c0 * 16 : nullptr, st)) return -1;
     // K-D
-    if (launch_length_regulate(w.xe, w.sigma, w.dur, bc, dw.dec_pos, w.xd, S2S_L_DEC_PAD, w.sigma_ext, w.total,
+    if (launch_length_regulate(w.xe, w.sigma, w.dur, bc, dw.dec_pos, w.xd, tc_path ? w.tcb.x16 : nullptr, S2S_L_DEC_PAD,
+                               w.sigma_ext, w.total,
                                taps && taps->lr_out_dev ? taps->lr_out_dev + c0 * S2S_L_DEC * 64 : nullptr, st)) return -1;
     if (taps) {
       if (tap_copy(taps->emb_out_dev ? taps->emb_out_dev + c0 * 16 * 64 : nullptr, w.emb, me * 64 * 4, st)) return -1;
@@ -438,7 +445,7 @@ int s2s_profile_kernel(s2s_handle h, int enable, double* ms_total, int64_t* laun
 
 int s2s_length_regulate(const float* x_dev, const float* sigma_dev, const int32_t* dur_dev, int64_t n_chunks,
                         float* out_dev, float* sigma_ext_dev, int32_t* total_dev, s2s_stream stream) {
-  return launch_length_regulate(x_dev, sigma_dev, dur_dev, n_chunks, nullptr, out_dev, S2S_L_DEC, sigma_ext_dev,
+  return launch_length_regulate(x_dev, sigma_dev, dur_dev, n_chunks, nullptr, out_dev, nullptr, S2S_L_DEC, sigma_ext_dev,
                                 total_dev, nullptr, static_cast<cudaStream_t>(stream));
 }
 

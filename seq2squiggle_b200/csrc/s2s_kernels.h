@@ -39,7 +39,7 @@ int launch_chunk_map(const int64_t* read_offsets, const int64_t* chunk_offsets, 
                      int32_t k, int32_t* chunk_read, int64_t* chunk_base, int32_t* chunk_nk, cudaStream_t st);
 // Tokenise (bases or codes) + src_emb + ReLU + prenet + ReLU -> emb_out; x_enc = emb_out + pos.
 int launch_embed(const DevWeights& w, const uint8_t* bases, const int64_t* chunk_base, const int32_t* chunk_nk,
-                 const int8_t* codes, int64_t n_chunks, float* emb_out, float* x_enc, cudaStream_t st);
+                 const int8_t* codes, int64_t n_chunks, float* emb_out, float* x_enc, __half* x_enc16, cudaStream_t st);
 
 // ---- k_simt.cu (fp32 CUDA-core path) --------------------------------------------------------
 enum { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_RES_LN = 2 };
@@ -49,6 +49,8 @@ int launch_linear_f32(const float* X, const float* Wt, const float* b, const flo
 // softmax(QK^T/sqrt(8))V per (chunk, head); qkv is [rows,192] (q|k|v), out [rows,64].
 // L = 16 (rows_per_chunk 16) or 250 (rows_per_chunk 256: pad rows are neither keys nor written... they are zeroed)
 int launch_attention_f32(const float* qkv, float* out, int64_t n_chunks, int L, int rows_per_chunk, cudaStream_t st);
+// encoder attention (fp32 math) with fp16 output: the A operand of the tensor-core fc GEMM
+int launch_attention_enc_f16out(const float* qkv, __half* out, int64_t n_chunks, cudaStream_t st);
 
 // ---- k_samplers.cu ---------------------------------------------------------------------------
 // h3 [M,192] = ReLU(first layers) already computed; this applies the 64->1 heads, Softplus, clamps,
@@ -61,8 +63,8 @@ int launch_sampler_heads(const DevWeights& w, const float* h3, int64_t n_kmers, 
 // x_dec[c, t, :] = (t < total ? enc_out[c, j(t), :] : 0) + dec_pos[t]  for t < 250, 0 for the 6 pad rows.
 // dec_pos == nullptr gives the plain LR output with row stride `rows_per_chunk_out` (stage entry point).
 int launch_length_regulate(const float* enc_out, const float* sigma, const int32_t* dur, int64_t n_chunks,
-                           const float* dec_pos, float* x_dec, int rows_per_chunk_out, float* sigma_ext,
-                           int32_t* total, float* lr_tap, cudaStream_t st);
+                           const float* dec_pos, float* x_dec, __half* x_dec16, int rows_per_chunk_out,
+                           float* sigma_ext, int32_t* total, float* lr_tap, cudaStream_t st);
 
 // ---- k_epilogue.cu ----------------------------------------------------------------------------
 // p = ReLU(y . w_out + b); pA = clamp(165 p + noise, 0).  y has 256 rows per chunk, outputs 250 per chunk.

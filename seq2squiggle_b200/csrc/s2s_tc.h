@@ -21,6 +21,8 @@ struct TcState {
 struct TcBuffers {
   __half* x16 = nullptr;    // [rows,64]  fp16 copy of the residual stream (GEMM A operand)
   __half* o16 = nullptr;    // [rows,64]  attention output (A operand of fc)
+  __half* xe16 = nullptr;   // encoder: [chunks*16 (padded to 128), 64] fp16 residual-stream copy
+  __half* oe16 = nullptr;   // encoder attention output
 };
 
 void tc_carve(TcBuffers& b, char* base, int64_t& off, int64_t batch_chunks);
@@ -30,6 +32,9 @@ void tc_destroy(TcState& s);
 int tc_profile(TcState& s, int enable, double* ms_total, int64_t* launches, int64_t* chunks);
 // Synchronises the stream and reports a device-side barrier timeout, if any.
 int tc_check_status(TcState& s, cudaStream_t st);
+// Runs all encoder layers in place on x32/x16 ([chunks*16 rows, padded to 128]); qkv32 [rows,192], o16 [rows,64] scratch.
+int tc_encoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, __half* x16, float* qkv32, __half* o16,
+               int64_t n_chunks, cudaStream_t st);
 int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, int64_t n_chunks, cudaStream_t st);
 
 }  // namespace s2s

@@ -72,7 +72,8 @@ def test_forward_chunks_matches_reference_stages(golden_dir, tag, ckpt, precisio
     t = {k: v.cpu().numpy() for k, v in taps.items()}
     assert np.array_equal(t["dur_int"], fx["dur_i"])                       # integer: bit-exact
     np.testing.assert_allclose(t["emb_out"], fx["emb_out"], rtol=0, atol=2e-5)
-    np.testing.assert_allclose(t["enc_out"], fx["enc_out"], rtol=0, atol=1e-4)
+    # encoder: fp32 CUDA cores in "fp32"; tensor cores with fp16 operands in "fp16" (|enc_out| ~ 1)
+    np.testing.assert_allclose(t["enc_out"], fx["enc_out"], rtol=0, atol=1e-4 if precision == "fp32" else 1e-2)
     np.testing.assert_allclose(t["sigma"], fx["sigma"], rtol=0, atol=2e-5)
     # expansion is an exact row copy of OUR enc_out: check indices through the values
     j = orc.lr_expand_indices(fx["dur_i"], 250)
