@@ -1,0 +1,270 @@
+"""Read source of ``seq2squiggle predict``: FASTA/FASTQ parsing, read mode and reference-mode sampling.
+
+Mirrors ``utils.py:290-671`` of the reference (``get_reads`` and everything under it).  The reference leans on
+``pysam.FastxFile`` and one ``scipy.stats`` ``rvs`` call per read; neither is needed here:
+
+* ``read_fasta`` is a small FASTA/FASTQ (optionally gzip) parser with FastxFile's semantics (name = first word of
+  the header line, multi-line FASTA sequences are joined, sequence returned verbatim — no upper-casing);
+* the read-length draws use ``numpy.random.RandomState(seed)`` directly, which is what ``scipy.stats.*.rvs(...,
+  random_state=<int>)`` does internally, so a given ``--seed`` yields the *same reads* as the reference
+  (pinned by ``tests/test_reads.py`` against scipy and against ``tests/golden/read_sampling.json``, which was
+  produced by the reference's own ``utils.sampling``).
+
+The Python ``random`` call order of ``utils.py:415-479`` (start position, strand, N replacement) is kept, since the
+module-level generator is seeded once by ``set_seeds`` (``utils.py:722-741``).
+"""
+from __future__ import annotations
+
+import gzip
+import logging
+import os
+import random
+import re
+from typing import Generator, Iterable, List, Sequence, Tuple
+from uuid import uuid4
+
+import numpy as np
+
+logger = logging.getLogger("seq2squiggle")
+
+
+# --------------------------------------------------------------------------------------------------
+# FASTA / FASTQ
+# --------------------------------------------------------------------------------------------------
+def _open_text(path):
+    path = str(path)
+    with open(path, "rb") as fh:
+        magic = fh.read(2)
+    if magic == b"\x1f\x8b":
+        return gzip.open(path, "rt", encoding="latin-1", newline=None)
+    return open(path, "r", encoding="latin-1", newline=None)
+
+
+def read_fasta(path, rna: bool = False) -> Generator[Tuple[str, str], None, None]:
+    """utils.py:290-308: yields ``(sequence, name)`` for every FASTA or FASTQ record of ``path``."""
+    with _open_text(path) as fh:
+        name, parts = None, []
+        line = fh.readline()
+        while line:
+            line = line.rstrip("\r\n")
+            if line.startswith(">"):
+                if name is not None:
+                    yield "".join(parts), name
+                name, parts = (line[1:].split() or [""])[0], []
+                line = fh.readline()
+            elif line.startswith("@") and name is None or (line.startswith("@") and not parts and name is None):
+                # FASTQ record: header, sequence line(s) up to '+', then as many quality characters
+                qname = (line[1:].split() or [""])[0]
+                seq_parts = []
+                line = fh.readline()
+                while line and not line.startswith("+"):
+                    seq_parts.append(line.strip())
+                    line = fh.readline()
+                seq = "".join(seq_parts)
+                qlen = 0
+                line = fh.readline()
+                while line and qlen < len(seq):
+                    qlen += len(line.rstrip("\r\n"))
+                    line = fh.readline()
+                yield seq, qname
+            else:
+                if name is not None:
+                    parts.append(line.strip())
+                line = fh.readline()
+        if name is not None:
+            yield "".join(parts), name
+
+
+def load_genome(fasta) -> Generator[str, None, None]:
+    """utils.py:586-589."""
+    for seq, _ in read_fasta(fasta):
+        yield str(seq)
+
+
+def process_genome(genome_seq: str) -> Tuple[str, int]:
+    """utils.py:592-595: upper-case, everything outside ACGT becomes N."""
+    genome_seq = re.sub(r"[^ATCG]", "N", genome_seq.upper())
+    return genome_seq, len(genome_seq)
+
+
+def preprocess_genome(fasta):
+    """utils.py:608-638 (the reference maps over a process pool; the result is the same)."""
+    logger.debug("Preprocessing the genome")
+    results = [process_genome(s) for s in load_genome(fasta)]
+    if not results:
+        raise ValueError(f"No sequences found in {fasta}")
+    seqs, lens = zip(*results)
+    logger.debug("Preprocessing the genome finished.")
+    return seqs, lens
+
+
+def compute_totals(generator) -> Tuple[int, int]:
+    """utils.py:598-605."""
+    total_reads = total_length = 0
+    for sequence, _ in generator:
+        total_reads += 1
+        total_length += len(sequence)
+    return total_reads, total_length
+
+
+# --------------------------------------------------------------------------------------------------
+# read-length laws (utils.py:311-331).  scipy's rvs(size=1, random_state=int) == RandomState(int) draw below.
+# --------------------------------------------------------------------------------------------------
+def draw_gamma_dis(mean, seed, total_len):
+    x = np.random.RandomState(seed).standard_gamma(6.3693711, size=1) + 0.53834893      # st.gamma.rvs(a, loc)
+    sample = int((x * mean / 4.39)[0])
+    return np.clip(sample, 1, total_len)
+
+
+def draw_beta_dis(mean, seed, total_len):
+    x = np.random.RandomState(seed).beta(1.778, 7.892, size=1) * 34191.257 + 316.758    # st.beta.rvs(a, b, loc, scale)
+    sample = (x[0] * mean / 6615.0).astype(int)
+    return np.clip(sample, 1, total_len)
+
+
+def draw_expon_dis(mean, seed, total_len):
+    x = np.random.RandomState(seed).standard_exponential(size=1) * 6972.5319847131141 + 213.98910256668592
+    sample = (x[0] * mean / 7106.0).astype(int)
+    return np.clip(sample, 1, total_len)
+
+
+DISTR_FUNCS = {"beta": draw_beta_dis, "gamma": draw_gamma_dis, "expon": draw_expon_dis}
+
+
+def get_genome_and_position(genome_lengths: Sequence[int], random_position: int) -> Tuple[int, int]:
+    """utils.py:359-371."""
+    total_length = sum(genome_lengths)
+    if random_position >= total_length:
+        raise ValueError("Random position exceeds the total length of genomes")
+    cumulative = 0
+    for i, length in enumerate(genome_lengths):
+        cumulative += length
+        if random_position < cumulative:
+            return i, random_position - (cumulative - length)
+    raise ValueError("Random position exceeds the total length of genomes")
+
+
+def read_check(read: str, read_length: int, read_i: int, profile: str, min_read_len: int = 30) -> bool:
+    """utils.py:381-398."""
+    if profile.startswith("dna") and len(read) != read_length:
+        logger.debug(f"Sampled Read length ({len(read)}) of read {read_i} is shorter than real read length ({read_length}).")
+        return False
+    if len(read) < min_read_len:
+        logger.debug(f"Sampled Read length ({len(read)}) of read {read_i} is shorter than the minimal read length ({min_read_len}).")
+        return False
+    count_n = read.count("N")
+    if count_n > 0.1 * read_length:
+        logger.debug(f"Too many 'N' bases ({count_n} out of {read_length}) for read {read_i}")
+        return False
+    return True
+
+
+def N_to_ACTG(read: str) -> str:
+    """utils.py:401-402 (one ``random.choice`` per N, in order)."""
+    return "".join(random.choice("ACGT") if base == "N" else base for base in read)
+
+
+_COMPLEMENT = str.maketrans("ATCG", "TAGC")
+
+
+def reverse_complement(f: str) -> str:
+    """utils.py:409-412: A<->T, C<->G, everything else unchanged."""
+    return f.translate(_COMPLEMENT)[::-1]
+
+
+def sampling(num_seqs, genome_seqs, genome_lens, r, seed, total_len, distr, profile, min_read_len=30,
+             max_retries=20) -> List[str]:
+    """utils.py:415-479: sample ``num_seqs`` reads from the genome(s)."""
+    draw = DISTR_FUNCS[distr]
+    total_genome_len = sum(genome_lens)
+    sampled = []
+    dna = profile.startswith("dna")
+    for read_i in range(num_seqs):
+        retries = 0
+        while retries < max_retries:
+            start_pos = random.randint(0, total_genome_len - 1)
+            genome_index, start_index = get_genome_and_position(genome_lens, start_pos)
+            genome = genome_seqs[genome_index]
+            unique_seed = seed + read_i * (max_retries + 1) + retries
+            read_length = int(draw(r, unique_seed, total_len)) if r > 0 else len(genome)
+            read = genome[start_index:start_index + read_length]
+            read_strand = random.choice("+-") if dna else "+"
+            if read_check(read, read_length, read_i, profile, min_read_len):
+                if "N" in read:
+                    read = N_to_ACTG(read)
+                if read_strand == "-":
+                    read = reverse_complement(read)
+                sampled.append(read)
+                break
+            retries += 1
+            if retries >= max_retries:
+                logger.debug(f"Failed to sample a valid read after {max_retries} retries for read {read_i}. Skipping this read.")
+            else:
+                logger.debug(f"Retrying to sample read {read_i} (attempt {retries + 1}/{max_retries})")
+    return sampled
+
+
+def export_fasta(read_l: Iterable[str], fasta) -> str:
+    """utils.py:480-486 (the reference writes the uuid without a '>' prefix; kept)."""
+    file_name, _ = os.path.splitext(str(fasta))
+    out_file = f"{file_name}_reads.fasta"
+    with open(out_file, "w") as f:
+        for read in read_l:
+            f.write(f"{str(uuid4())}\n{''.join(read)}\n")
+    return out_file
+
+
+def yield_reads(reads: Iterable[str]):
+    """utils.py:489-490."""
+    return ((read, str(uuid4())) for read in reads)
+
+
+def sample_reads_from_reference(genome_seqs, genome_lens, n, r, c, config, fasta, seed, save=False, distr="expon",
+                                profile="dna-r10-min", min_read_len=30):
+    """utils.py:493-582: argument validation (same messages) + sampling."""
+    logger.debug("Generating reads from the reference input file.")
+    if n <= 0 and c <= 0:
+        logger.error("You need to specify the coverage c or the number of reads n")
+        raise ValueError("You need to specify the coverage c or the number of reads n")
+    if n != -1 and c != -1:
+        logger.error("You can only either specify the coverage c or the number of reads, but not both")
+        raise ValueError("You can only either specify the coverage c or the number of reads, but not both")
+    if r <= 0:
+        logger.error("You need to specify an average read length r for sampling from the reads from the reference sequence.")
+        raise ValueError("You need to specify the read length r")
+    total_len = sum(len(seq) for seq in genome_seqs)
+    avg_genome_len = total_len / len(genome_seqs)
+    seq_num = n if n != -1 else round(c * total_len / r)
+    logger.debug(f"Number of reads: {seq_num}")
+    if r > avg_genome_len and profile.startswith("dna"):
+        logger.warning(
+            f"Average reference sequence length ({avg_genome_len:.2f}) is smaller than the desired average read length ({r})."
+            " If the sampled read length is higher than the reference sequence length, they will be skipped."
+            " Consider reducing the desired average read length via -r.")
+    read_list = sampling(seq_num, genome_seqs, genome_lens, r, seed, total_len, distr, profile, min_read_len)
+    total_l = sum(round(len(read) / config["max_dna_len"]) for read in read_list)
+    reads_fasta = export_fasta(read_list, fasta) if save else yield_reads(read_list)
+    logger.debug("Generating reads finished.")
+    return reads_fasta, total_l
+
+
+def get_reads(fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len, save=False):
+    """utils.py:641-671: ``(generator of (sequence, name), length hint)``."""
+    logger.info(f"{'Read' if read_input else 'Reference'} mode.")
+    is_rna = profile.startswith("rna")
+    if read_input:
+        if n <= 0:  # every read exactly once
+            return read_fasta(fasta, is_rna), compute_totals(read_fasta(fasta, is_rna))[1]
+        all_reads = list(read_fasta(fasta, is_rna))
+        rng = random.Random(seed)
+        sampled = [rng.choice(all_reads) for _ in range(n)]
+
+        def generator():
+            for seq, _ in sampled:
+                yield seq, str(uuid4())
+
+        return generator(), sum(round(len(seq) / config["max_dna_len"]) for seq, _ in sampled)
+    genome_seqs, genome_lens = preprocess_genome(fasta)
+    reads_fasta, total_l = sample_reads_from_reference(genome_seqs, genome_lens, n, r, c, config, fasta, seed, save,
+                                                       distr, profile, min_read_len)
+    return read_fasta(reads_fasta, is_rna) if save else (reads_fasta, total_l)
