@@ -40,11 +40,18 @@ class S2STaps(C.Structure):
     _fields_ = [(name + "_dev", C.c_void_p) for name in TAP_FIELDS]
 
 
+BLOW5_LIB_PATH = os.path.join(HERE, "libs2s_blow5.so")
+BLOW5_SOURCE = "blow5_writer.cpp"
+EXPORTS_BLOW5 = ["s2s_blow5_last_error", "s2s_blow5_open", "s2s_blow5_write_batch", "s2s_blow5_bytes_written",
+                 "s2s_blow5_close"]
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "s2s_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f != BLOW5_SOURCE] + \
+           [os.path.join(HERE, "..", "include", "s2s_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
@@ -59,6 +66,48 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         sys.stderr.write(res.stderr)
     return LIB_PATH
+
+
+def build_blow5(force: bool = False) -> str:
+    """Compile the native SLOW5/BLOW5 writer (host C++, zlib) into the in-tree ``libs2s_blow5.so``."""
+    src, hdr = os.path.join(CSRC, BLOW5_SOURCE), os.path.join(HERE, "..", "include", "s2s_blow5.h")
+    if not force and os.path.exists(BLOW5_LIB_PATH) and \
+            os.path.getmtime(BLOW5_LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return BLOW5_LIB_PATH
+    cmd = ["g++", "-O3", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", BLOW5_LIB_PATH, src, "-lz"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ (blow5_writer) failed:\n" + res.stdout + res.stderr)
+    return BLOW5_LIB_PATH
+
+
+_blow5 = None
+
+
+def load_blow5() -> C.CDLL:
+    global _blow5
+    if _blow5 is not None:
+        return _blow5
+    if not os.path.exists(BLOW5_LIB_PATH):
+        raise RuntimeError(f"{BLOW5_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(BLOW5_LIB_PATH)
+    vp, i64, i32, f64 = C.c_void_p, C.c_int64, C.c_int32, C.c_double
+    lib.s2s_blow5_last_error.restype = C.c_char_p
+    lib.s2s_blow5_open.restype = C.c_int
+    lib.s2s_blow5_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(vp)]
+    lib.s2s_blow5_write_batch.restype = C.c_int
+    lib.s2s_blow5_write_batch.argtypes = [vp, i64, C.c_char_p, vp, vp, vp, vp, vp, vp, f64, f64, f64, i32]
+    lib.s2s_blow5_bytes_written.restype = i64
+    lib.s2s_blow5_bytes_written.argtypes = [vp]
+    lib.s2s_blow5_close.restype = C.c_int
+    lib.s2s_blow5_close.argtypes = [vp]
+    _blow5 = lib
+    return lib
+
+
+def check_blow5(status: int, what: str) -> None:
+    if status != 0:
+        raise RuntimeError(f"{what} failed ({status}): {load_blow5().s2s_blow5_last_error().decode('utf-8', 'replace')}")
 
 
 _lib = None
@@ -100,6 +149,8 @@ def load() -> C.CDLL:
     lib.s2s_digitise.argtypes = [vp, i64, f32, f32, f32, vp, vp]
     lib.s2s_compact_reads.restype = C.c_int
     lib.s2s_compact_reads.argtypes = [vp, vp, i64, i64, f32, f32, f32, i32, vp, i64, vp, vp, vp]
+    lib.s2s_profile_kernel.restype = C.c_int
+    lib.s2s_profile_kernel.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i64)]
     if lib.s2s_abi_version() != 1:
         raise RuntimeError("libs2s_b200.so ABI version mismatch; rebuild")
     _lib = lib

@@ -52,7 +52,7 @@ def read_fasta(path, rna: bool = False) -> Generator[Tuple[str, str], None, None
                     yield "".join(parts), name
                 name, parts = (line[1:].split() or [""])[0], []
                 line = fh.readline()
-            elif line.startswith("@") and name is None or (line.startswith("@") and not parts and name is None):
+            elif line.startswith("@") and name is None:
                 # FASTQ record: header, sequence line(s) up to '+', then as many quality characters
                 qname = (line[1:].split() or [""])[0]
                 seq_parts = []

@@ -1,0 +1,67 @@
+"""Independent SLOW5/BLOW5 reader (test infrastructure): parses a file from the published SLOW5 v0.2.0 layout with
+``struct`` only, sharing no code with csrc/blow5_writer.cpp."""
+import struct
+import zlib
+
+
+def read_blow5(path):
+    data = open(path, "rb").read()
+    assert data[:6] == b"BLOW5\x01", "magic"
+    version = tuple(data[6:9])
+    rec_comp = data[9]
+    (n_groups,) = struct.unpack_from("<I", data, 10)
+    sig_comp = data[14]
+    assert data[15:64] == b"\0" * 49, "padding"
+    (hsize,) = struct.unpack_from("<I", data, 64)
+    ascii_hdr = data[68:68 + hsize].decode()
+    lines = ascii_hdr.split("\n")
+    assert lines[-1] == ""
+    attrs = dict(l[1:].split("\t", 1) for l in lines if l.startswith("@"))
+    types = [l for l in lines if l.startswith("#")][0][1:].split("\t")
+    names = [l for l in lines if l.startswith("#")][1][1:].split("\t")
+    assert len(types) == len(names)
+    pos, records = 68 + hsize, []
+    assert data[-5:] == b"5WOLB", "eof marker"
+    while pos < len(data) - 5:
+        (size,) = struct.unpack_from("<Q", data, pos)
+        pos += 8
+        body = data[pos:pos + size]
+        pos += size
+        if rec_comp == 1:
+            body = zlib.decompress(body)
+        q = 0
+        (idl,) = struct.unpack_from("<H", body, q); q += 2
+        rid = body[q:q + idl].decode(); q += idl
+        (group,) = struct.unpack_from("<I", body, q); q += 4
+        dig, off, rng, rate = struct.unpack_from("<dddd", body, q); q += 32
+        (n,) = struct.unpack_from("<Q", body, q); q += 8
+        sig = struct.unpack_from(f"<{n}h", body, q); q += 2 * n
+        (cl,) = struct.unpack_from("<Q", body, q); q += 8
+        chan = body[q:q + cl].decode(); q += cl
+        (med,) = struct.unpack_from("<d", body, q); q += 8
+        (rnum,) = struct.unpack_from("<i", body, q); q += 4
+        (mux,) = struct.unpack_from("<B", body, q); q += 1
+        (stime,) = struct.unpack_from("<Q", body, q); q += 8
+        assert q == len(body), "record size"
+        records.append(dict(read_id=rid, read_group=group, digitisation=dig, offset=off, range=rng, sampling_rate=rate,
+                            len_raw_signal=n, signal=list(sig), channel_number=chan, median_before=med,
+                            read_number=rnum, start_mux=mux, start_time=stime))
+    assert pos == len(data) - 5
+    return dict(version=version, record_compression=rec_comp, signal_compression=sig_comp, num_read_groups=n_groups,
+                attrs=attrs, types=types, names=names, records=records)
+
+
+def read_slow5(path):
+    lines = open(path).read().split("\n")
+    assert lines[0] == "#slow5_version\t0.2.0" and lines[1] == "#num_read_groups\t1"
+    attrs = dict(l[1:].split("\t", 1) for l in lines if l.startswith("@"))
+    hdr = [l for l in lines[2:] if l.startswith("#")]
+    names = hdr[1][1:].split("\t")
+    recs = []
+    for l in lines:
+        if not l or l[0] in "#@":
+            continue
+        f = dict(zip(names, l.split("\t")))
+        f["signal"] = [int(x) for x in f.pop("raw_signal").split(",")]
+        recs.append(f)
+    return dict(attrs=attrs, names=names, records=recs)

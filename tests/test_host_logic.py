@@ -1,0 +1,176 @@
+"""CPU tests of the host side: the C-ABI libraries load and export every symbol the headers declare (no compute
+call is made without a GPU), option plumbing (profiles, run options, CLI defaults), read batching / sharding and
+the BLOW5 part merge of the multi-GPU path."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(s2s_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    from seq2squiggle_b200 import _lib
+    _lib.build()
+    _lib.build_blow5()
+    for header, path, listed in (("s2s_b200.h", _lib.LIB_PATH, _lib.EXPORTS), ("s2s_blow5.h", _lib.BLOW5_LIB_PATH, _lib.EXPORTS_BLOW5)):
+        declared = _declared(header)
+        assert declared and sorted(listed) == declared, (header, set(declared) ^ set(listed))
+        lib = ctypes.CDLL(path)
+        for name in declared:
+            assert hasattr(lib, name), f"{path} does not export {name}"
+    lib = _lib.load()
+    assert lib.s2s_abi_version() == 1
+    assert lib.s2s_chunks_of_read(1000, 9) == 62 and lib.s2s_chunks_of_read(8, 9) == 0 and lib.s2s_chunks_of_read(9, 9) == 1
+    cfg = _lib.S2SConfig(9, 2, 2, 1, 64, 256, 8, 16, 250, 165.0)
+    assert lib.s2s_weights_count(ctypes.byref(cfg)) == 233_025 - 0 or lib.s2s_weights_count(ctypes.byref(cfg)) > 200_000
+    bad = _lib.S2SConfig(9, 2, 2, 1, 128, 256, 8, 16, 250, 165.0)
+    assert lib.s2s_weights_count(ctypes.byref(bad)) == -1 and b"unsupported architecture" in lib.s2s_last_error()
+
+
+def test_create_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this box has a GPU")
+    from seq2squiggle_b200.checkpoint import random_init_checkpoint, set_config
+    from seq2squiggle_b200.engine import Engine
+    cfg = set_config(None)
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        Engine(random_init_checkpoint(cfg, 1)["state_dict"], cfg)
+
+
+def test_weight_blob_matches_parameter_count():
+    from seq2squiggle_b200 import _lib
+    from seq2squiggle_b200.checkpoint import pack_weights, random_init_checkpoint, set_config
+    for k in (9, 6):
+        cfg = set_config(None)
+        cfg["seq_kmer"] = k
+        sd = random_init_checkpoint(cfg, 1)["state_dict"]
+        blob = pack_weights(sd, cfg)
+        c = _lib.S2SConfig(k, 2, 2, 1, 64, 256, 8, 16, 250, 165.0)
+        assert blob.size == _lib.load().s2s_weights_count(ctypes.byref(c)) == sum(v.numel() for v in sd.values())
+        with pytest.raises(KeyError):
+            pack_weights({kk: v for kk, v in sd.items() if "w_qs" not in kk}, cfg)
+
+
+def test_run_options_branch_mapping():
+    """modules.py:410-432 / model.py:224-238 branch selection and inference.py:358-364 derived values."""
+    from seq2squiggle_b200.engine import DUR_CONSTANT, DUR_NORMAL, DUR_SAMPLER, NOISE_OFF, NOISE_SAMPLER, NOISE_STATIC, RunOptions
+    from seq2squiggle_b200.profiles import get_profile, update_config, update_profile
+    for name, dwell in (("dna-r10-prom", 12.5), ("dna-r9-min", 4000 / 450), ("rna-004-min", 4000 / 130)):
+        o = RunOptions.from_profile(get_profile(name), name, duration_sampling=False, dwell_std=0.0, noise_std=0.0)
+        c = o.to_c(5)
+        assert abs(c.dwell_mean - dwell) < 1e-5 and c.duration_mode == DUR_CONSTANT and c.noise_mode == NOISE_OFF
+        assert c.rna_reverse == int(name.startswith("rna")) and c.chunk_id_base == 5
+    p = get_profile("dna-r10-prom")
+    assert RunOptions.from_profile(p, "dna-r10-prom", duration_sampling=False, dwell_std=1.5).to_c().duration_mode == DUR_NORMAL
+    assert RunOptions.from_profile(p, "dna-r10-prom", duration_sampling=True, dwell_std=1.5).to_c().duration_mode == DUR_SAMPLER
+    assert RunOptions.from_profile(p, "dna-r10-prom", noise_std=2.0, noise_sampling=False).to_c().noise_mode == NOISE_STATIC
+    assert RunOptions.from_profile(p, "dna-r10-prom", noise_std=2.0, noise_sampling=True).to_c().noise_mode == NOISE_SAMPLER
+    assert RunOptions.from_profile(p, "dna-r10-prom", noise_std=-1, noise_sampling=True).to_c().noise_mode == NOISE_OFF
+    up = update_profile(get_profile("dna-r10-prom"), digitisation=4096, bps=None, range=300.0)
+    assert up["digitisation"] == 4096 and up["bps"] == 400 and up["range"] == 300.0
+    assert update_config("dna-r9-prom", {})["seq_kmer"] == 6 and update_config("rna-004-min", {})["seq_kmer"] == 9
+    with pytest.raises(ValueError):
+        update_config("dna-r7", {})
+
+
+def test_cli_surface_matches_reference_defaults():
+    from click.testing import CliRunner
+    from seq2squiggle_b200.cli import main, predict
+    opts = {o.name: o for o in predict.params}
+    expect = dict(read_input=False, num_reads=-1, read_length=1000, coverage=-1, profile="dna-r10-prom",
+                  noise_sampler=True, duration_sampler=True, dwell_mean=None, dwell_std=0.0, noise_std=2.0,
+                  distr="expon", predict_batch_size=1024, export_every_n_samples=1000000, sample_rate=None, bps=None,
+                  digitisation=None, range_val=None, offset_mean=None, offset_std=None, median_before_mean=None,
+                  median_before_std=None, min_noise=0.0, min_duration=3, min_read_len=30, preserve_read_ids=False,
+                  seed=0, model=None, config=None, verbosity="info")
+    for name, default in expect.items():
+        assert name in opts, name
+        assert opts[name].default == default, (name, opts[name].default)
+    assert "--noise-sampling" in opts["noise_sampler"].opts and "--noise-sampler" in opts["noise_sampler"].opts
+    assert "--duration-sampling" in opts["duration_sampler"].opts
+    assert opts["profile"].type.convert("dna_r9_min", None, None) == "dna-r9-min"     # README spelling
+    r = CliRunner().invoke(main, ["predict"])
+    assert r.exit_code == 1                                                          # seq2squiggle.py:513-515
+    r = CliRunner().invoke(main, ["predict", "--show-advanced-options"])
+    assert r.exit_code == 0 and "--min_duration" in r.output and "--range_val" in r.output
+    assert CliRunner().invoke(main, ["train"]).exit_code != 0
+
+
+def test_inference_run_boundary_errors(tmp_path):
+    """Errors raised before any device work keep the reference's types/messages (inference.py:80-82, utils.py:257-262)."""
+    from seq2squiggle_b200.checkpoint import check_model, set_config
+    from seq2squiggle_b200.inference import get_saved_weights, get_writer
+    from seq2squiggle_b200.profiles import get_profile
+    p = get_profile("dna-r10-prom")
+    with pytest.raises(ValueError, match=r"\.pod5, \.slow5, or \.blow5"):
+        get_writer(str(tmp_path / "x.fast5"), p, True, 1000, "dna-r10-prom", False)
+    existing = tmp_path / "sub" / "o.blow5"
+    os.makedirs(existing.parent)
+    existing.write_text("old")
+    w, n = get_writer(str(existing), p, True, 1000, "dna-r10-prom", False)
+    assert not existing.exists() and n == 1000 and type(w).__name__ == "BLOW5Writer"
+    w, n = get_writer(str(tmp_path / "o.pod5"), p, True, 1000, "dna-r10-prom", False)
+    assert n == float("inf") and type(w).__name__ == "POD5Writer"
+    with pytest.raises(PermissionError):
+        get_saved_weights("dna-r10-prom")
+    cfg = set_config(None)
+    other = dict(cfg, seq_kmer=6)
+    with pytest.raises(ValueError, match="seq_kmer"):
+        check_model(other, cfg)
+    check_model(dict(cfg, dff=128), cfg)   # other mismatches only warn
+
+
+def test_batching_and_sharding():
+    from seq2squiggle_b200.inference import batch_reads, chunks_of_read, shard_reads
+    rng = np.random.default_rng(0)
+    lens = rng.integers(1, 4000, size=500)
+    reads = [("A" * int(l), f"r{i}") for i, l in enumerate(lens)]
+    batches = list(batch_reads(reads, 9, batch_chunks=2000))
+    assert [x for b in batches for x in b] == reads                     # order kept, nothing split or lost
+    sizes = [sum(chunks_of_read(len(s), 9) for s, _ in b) for b in batches]
+    assert all(s >= 2000 for s in sizes[:-1]) and max(sizes) < 2000 + 250
+    counts = [chunks_of_read(int(l), 9) for l in lens]
+    for world in (1, 2, 3, 8):
+        sh = shard_reads(counts, world)
+        assert sh[0][0] == 0 and sh[-1][1] == len(counts)
+        assert all(sh[i][1] == sh[i + 1][0] for i in range(world - 1))  # contiguous, disjoint, complete
+        per = [sum(counts[a:b]) for a, b in sh]
+        assert max(per) - min(per) <= 2 * max(counts)                 # each boundary is within one read of ideal
+    assert shard_reads([], 4) == [(0, 0)] * 4
+    assert shard_reads([5], 2) in ([(0, 0), (0, 1)], [(0, 1), (1, 1)])
+
+
+def test_merge_blow5_parts_equals_single_writer(tmp_path):
+    from seq2squiggle_b200.inference import merge_blow5_parts
+    from seq2squiggle_b200.profiles import get_profile
+    from seq2squiggle_b200.signal_io import BLOW5Writer
+    from tests.blow5_reader import read_blow5
+    rng = np.random.default_rng(3)
+    prof = get_profile("dna-r10-prom")
+    sigs = {f"r{i}": rng.integers(-100, 900, size=int(rng.integers(1, 300))).astype(np.int16) for i in range(11)}
+    names = list(sigs)
+    single = BLOW5Writer(str(tmp_path / "single.blow5"), prof, True, "dna-r10-prom", False)
+    single.signals = sigs
+    single.save()
+    parts = []
+    for r, (lo, hi) in enumerate(((0, 4), (4, 4), (4, 11))):             # middle rank owns no reads
+        w = BLOW5Writer(str(tmp_path / f"o.blow5.part{r}"), prof, True, "dna-r10-prom", False)
+        w.signals = {n: sigs[n] for n in names[lo:hi]}
+        w.save()
+        parts.append(w.filename)
+    nr, ns = merge_blow5_parts(str(tmp_path / "o.blow5"), parts, preserve_read_ids=False)
+    a, b = read_blow5(str(tmp_path / "single.blow5")), read_blow5(str(tmp_path / "o.blow5"))
+    assert nr == 11 and ns == sum(len(v) for v in sigs.values())
+    assert a["records"] == b["records"]

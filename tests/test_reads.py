@@ -1,0 +1,96 @@
+"""Host read source (seq2squiggle_b200/reads.py) against the reference's own sampler output
+(tests/golden/read_sampling.json, produced by utils.sampling via oracle/make_golden.py) and against scipy."""
+import gzip
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from seq2squiggle_b200 import reads as R
+
+
+def test_sampling_matches_reference_golden(golden_dir):
+    fx = json.load(open(os.path.join(golden_dir, "read_sampling.json")))
+    genome = fx["genome"]
+    assert len(fx["cases"]) >= 3
+    for case in fx["cases"]:
+        random.seed(case["seed"])
+        got = R.sampling(case["n"], [genome], [len(genome)], case["r"], case["seed"], len(genome), case["distr"],
+                         case["profile"], 30)
+        assert [len(r) for r in got] == case["lens"], case["distr"]
+        assert [hashlib.md5(r.encode()).hexdigest() for r in got] == case["md5"], case["distr"]
+
+
+def test_length_draws_equal_scipy():
+    st = pytest.importorskip("scipy.stats")
+    for seed in (0, 1, 7, 12345, 2 ** 31 - 5):
+        e = st.expon.rvs(loc=213.98910256668592, scale=6972.5319847131141, size=1, random_state=seed)
+        assert R.draw_expon_dis(1000, seed, 10 ** 7) == np.clip((e[0] * 1000 / 7106.0).astype(int), 1, 10 ** 7)
+        g = st.gamma.rvs(6.3693711, 0.53834893, size=1, random_state=seed)
+        assert R.draw_gamma_dis(1000, seed, 10 ** 7) == np.clip(int((g * 1000 / 4.39)[0]), 1, 10 ** 7)
+        b = st.beta.rvs(1.778, 7.892, 316.758, 34191.257, size=1, random_state=seed)
+        assert R.draw_beta_dis(1000, seed, 10 ** 7) == np.clip((b[0] * 1000 / 6615.0).astype(int), 1, 10 ** 7)
+
+
+def test_fasta_fastq_parser(tmp_path):
+    fa = tmp_path / "a.fasta"
+    fa.write_text(">r1 desc here\nACGT\nacgtNN\n\n>r2\nTTTT\n>empty\n>r3\tx\nGG\r\nCC\r\n")
+    assert list(R.read_fasta(fa)) == [("ACGTacgtNN", "r1"), ("TTTT", "r2"), ("", "empty"), ("GGCC", "r3")]
+    fq = tmp_path / "b.fastq"
+    fq.write_text("@q1 comment\nACGTAC\n+\n@@@@II\n@q2\nGGA\nTT\n+q2\nII\nIII\n")
+    assert list(R.read_fasta(fq)) == [("ACGTAC", "q1"), ("GGATT", "q2")]
+    gz = tmp_path / "c.fasta.gz"
+    with gzip.open(gz, "wt") as fh:
+        fh.write(">g\nAC\nGT\n")
+    assert list(R.read_fasta(gz)) == [("ACGT", "g")]
+
+
+def test_example_files_shapes():
+    """SURVEY §8c integer facts about the reference's example reads (only if the reference tree is mounted)."""
+    path = "/root/reference/example/lamda_genome_reads.fasta"
+    if not os.path.exists(path):
+        pytest.skip("reference examples not present on this box")
+    lens = [len(s) for s, _ in R.read_fasta(path)]
+    assert lens == [2843, 10510, 8487, 2207, 11936, 4407, 1434, 2449, 14971, 11072]
+
+
+def test_genome_preprocessing_and_revcomp():
+    assert R.process_genome("acgtRYn-x") == ("ACGTNNNNN", 9)
+    assert R.reverse_complement("AACGTN") == "NACGTT"
+    assert R.read_check("ACGT" * 10, 40, 0, "dna-r10-prom", 30)
+    assert not R.read_check("ACGT" * 5, 40, 0, "dna-r10-prom", 30)       # cut short by the genome end
+    assert R.read_check("ACGT" * 10, 50, 0, "rna-004-prom", 30)          # RNA: length mismatch allowed
+    assert not R.read_check("N" * 5 + "A" * 35, 40, 0, "dna-r10-prom", 30)
+
+
+def test_get_reads_modes_and_errors(tmp_path):
+    cfg = {"max_dna_len": 16, "seq_kmer": 9}
+    fa = tmp_path / "g.fasta"
+    rng = np.random.default_rng(1)
+    fa.write_text(">chr\n" + "".join(rng.choice(list("ACGT"), 5000)) + "\n")
+    with pytest.raises(ValueError, match="coverage c or the number of reads n"):
+        R.get_reads(fa, False, -1, 1000, -1, cfg, "expon", 3, "dna-r10-prom", 30)
+    with pytest.raises(ValueError, match="not both"):
+        R.get_reads(fa, False, 5, 1000, 3, cfg, "expon", 3, "dna-r10-prom", 30)
+    with pytest.raises(ValueError, match="read length r"):
+        R.get_reads(fa, False, 5, 0, -1, cfg, "expon", 3, "dna-r10-prom", 30)
+    random.seed(3)
+    a = [s for s, _ in R.get_reads(fa, False, 25, 300, -1, cfg, "expon", 3, "dna-r10-prom", 30)[0]]
+    random.seed(3)
+    b = [s for s, _ in R.get_reads(fa, False, 25, 300, -1, cfg, "expon", 3, "dna-r10-prom", 30)[0]]
+    assert a == b and 0 < len(a) <= 25 and all(len(s) >= 30 for s in a)
+    random.seed(3)
+    cov, _ = R.get_reads(fa, False, -1, 500, 2, cfg, "expon", 3, "dna-r10-prom", 30)
+    assert len(list(cov)) <= round(2 * 5000 / 500)
+    # read mode: every read once, names preserved; with -n: sampled with replacement by random.Random(seed)
+    rd = tmp_path / "r.fasta"
+    rd.write_text(">a\nACGTACGTACGTAAA\n>b\nGGGGGGGGGGCCCCCCCCCCTTTT\n")
+    gen, total = R.get_reads(rd, True, -1, 1000, -1, cfg, "expon", 3, "dna-r10-prom", 30)
+    assert list(gen) == [("ACGTACGTACGTAAA", "a"), ("GGGGGGGGGGCCCCCCCCCCTTTT", "b")] and total == 39
+    gen, _ = R.get_reads(rd, True, 7, 1000, -1, cfg, "expon", 5, "dna-r10-prom", 30)
+    seqs = [s for s, _ in gen]
+    rr = random.Random(5)
+    assert seqs == [rr.choice(["ACGTACGTACGTAAA", "GGGGGGGGGGCCCCCCCCCCTTTT"]) for _ in range(7)]

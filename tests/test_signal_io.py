@@ -1,0 +1,108 @@
+"""SLOW5/BLOW5 writer (native libs2s_blow5.so behind seq2squiggle_b200.signal_io) read back with an independent
+parser; record fields as the reference fills them (signal_io.py:104-171)."""
+import os
+
+import numpy as np
+import pytest
+
+from seq2squiggle_b200.profiles import get_profile
+from seq2squiggle_b200.signal_io import BLOW5Writer, POD5Writer, get_seq_kit_and_flow_cell, indexed_uuid
+from tests.blow5_reader import read_blow5, read_slow5
+
+
+def _signals(rng, n, empty_at=()):
+    out = {}
+    for i in range(n):
+        ln = 0 if i in empty_at else int(rng.integers(1, 700))
+        out[f"read-{i}"] = rng.integers(-32768, 32767, size=ln).astype(np.int16)
+    return out
+
+
+@pytest.mark.parametrize("comp", ["none", "zlib"])
+def test_blow5_roundtrip_ideal_mode(tmp_path, comp):
+    rng = np.random.default_rng(0)
+    prof = get_profile("dna-r10-prom")
+    path = str(tmp_path / "o.blow5")
+    w = BLOW5Writer(path, prof, True, "dna-r10-prom", False, n_threads=3, record_compression=comp)
+    first = _signals(rng, 9, empty_at=(2,))
+    w.signals = first
+    w.save()
+    second = _signals(rng, 5)
+    second = {k + "b": v for k, v in second.items()}
+    w.signals = second                       # second flush appends (file exists -> mode 'a')
+    w.save()
+    f = read_blow5(path)
+    assert f["version"] == (0, 2, 0) and f["num_read_groups"] == 1 and f["signal_compression"] == 0
+    assert f["record_compression"] == (1 if comp == "zlib" else 0)
+    assert f["attrs"]["asic_id"] == "asic_id_0" and f["attrs"]["run_id"] == "run_id_0"
+    assert f["attrs"]["flow_cell_id"] == "FAN00000" and f["attrs"]["flow_cell_product_code"] == "FLO-PRO114"
+    assert f["attrs"]["experiment_type"] == "genomic_dna" and f["attrs"]["sample_frequency"] == "5000"
+    assert f["attrs"]["sequencing_kit"] == "SQK-LSK114" and "exp_start_time" in f["attrs"]
+    assert f["names"] == ["read_id", "read_group", "digitisation", "offset", "range", "sampling_rate", "len_raw_signal",
+                          "raw_signal", "channel_number", "median_before", "read_number", "start_mux", "start_time"]
+    allsig = [(i, v) for i, v in enumerate(list(first.values()) + list(second.values()))]
+    kept = [(i, v) for i, v in allsig if len(v)]
+    assert len(f["records"]) == len(kept) == 13
+    t = 0
+    for rec, (idx, sig) in zip(f["records"], kept):
+        assert rec["read_id"] == str(indexed_uuid(idx + 1))           # empty read 2 leaves a gap, like the reference
+        assert rec["read_number"] == idx and rec["read_group"] == 0 and rec["start_mux"] == 0
+        assert rec["channel_number"] == "0"
+        assert rec["digitisation"] == 2048.0 and rec["range"] == prof["range"] and rec["sampling_rate"] == 5000.0
+        assert rec["offset"] == prof["offset_mean"] and rec["median_before"] == prof["median_before_mean"]
+        assert rec["signal"] == sig.tolist() and rec["len_raw_signal"] == len(sig)
+        assert rec["start_time"] == t
+        t += len(sig)
+    assert w.samples_written == t and w.reads_written == 13
+
+
+def test_blow5_non_ideal_metadata_draws_and_preserved_ids(tmp_path):
+    prof = get_profile("rna-004-min")
+    path = str(tmp_path / "o.blow5")
+    w = BLOW5Writer(path, prof, False, "rna-004-min", True)
+    sig = _signals(np.random.default_rng(1), 4)
+    np.random.seed(42)
+    w.signals = sig
+    w.save()
+    np.random.seed(42)
+    exp = [(np.random.normal(prof["median_before_mean"], prof["median_before_std"]),
+            np.random.normal(prof["offset_mean"], prof["offset_std"])) for _ in sig]   # signal_io.py:131-133 order
+    f = read_blow5(path)
+    assert f["attrs"]["experiment_type"] == "rna" and f["attrs"]["sequencing_kit"] == "sqk-rna004"
+    assert f["attrs"]["flow_cell_product_code"] == "FLO-MIN004RA"
+    for rec, name, (med, off) in zip(f["records"], sig, exp):
+        assert rec["read_id"] == name and rec["median_before"] == med and rec["offset"] == off
+
+
+def test_slow5_ascii(tmp_path):
+    prof = get_profile("dna-r9-min")
+    path = str(tmp_path / "o.slow5")
+    w = BLOW5Writer(path, prof, True, "dna-r9-min", False)
+    sig = _signals(np.random.default_rng(2), 3)
+    w.signals = sig
+    w.save()
+    w.signals = {"x": np.array([1, -2, 3], dtype=np.int16)}
+    w.save()
+    f = read_slow5(path)
+    assert f["attrs"]["sequencing_kit"] == "SQK-LSK109" and len(f["records"]) == 4
+    for rec, s in zip(f["records"], list(sig.values()) + [np.array([1, -2, 3])]):
+        assert rec["signal"] == s.tolist() and int(rec["len_raw_signal"]) == len(s)
+        assert float(rec["range"]) == prof["range"] and float(rec["offset"]) == prof["offset_mean"]
+    assert f["records"][3]["read_number"] == "3" and f["records"][3]["read_id"] == str(indexed_uuid(4))
+
+
+def test_writer_errors_and_kits(tmp_path):
+    prof = get_profile("dna-r10-min")
+    w = BLOW5Writer(str(tmp_path / "e.blow5"), prof, True, "dna-r10-min", False)
+    with pytest.raises(ValueError, match="No signals were found"):
+        w.save()                                                       # signal_io.py:92-94
+    with pytest.raises(ValueError, match="No signals were found"):
+        POD5Writer(str(tmp_path / "e.pod5"), prof, True, "dna-r10-min", False).save()
+    w.signals = {"cpu_float": __import__("torch").zeros(4)}
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        w.save()                                                       # float pA must be digitised by the CUDA kernel
+    assert get_seq_kit_and_flow_cell("dna-r9-prom") == ("SQK-LSK109", "FLO-PRO001")
+    assert get_seq_kit_and_flow_cell("rna-004-prom") == ("sqk-rna004", "FLO-PRO004RA")
+    with pytest.raises(ValueError):
+        get_seq_kit_and_flow_cell("dna-r7-min")
+    assert str(indexed_uuid(12)) == "00000000-0000-0000-0000-000000000012"
