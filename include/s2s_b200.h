@@ -145,6 +145,10 @@ int s2s_compact_reads(const float* pa_dev /*[C,250]*/, const int64_t* chunk_offs
  * summed device time, the number of launches and the chunks they covered. */
 int s2s_profile_kernel(s2s_handle h, int enable, double* ms_total, int64_t* launches, int64_t* chunks);
 
+/* Developer hook: per-phase clock64() sums of the attention kernel (thread 0 of every CTA); all zero unless the
+ * library was built with -DS2S_PHASE_TIMING.  out[0..n): see csrc/k_tc.cu PHASE() indices.  Synchronises the device. */
+int s2s_debug_counters(int64_t* out, int32_t n, int32_t reset);
+
 /* Launch counter: number of kernels this library has launched since load (bench.py gpu_launches). */
 int64_t s2s_launch_count(void);
 

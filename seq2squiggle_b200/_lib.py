@@ -16,7 +16,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 EXPORTS = ["s2s_last_error", "s2s_abi_version", "s2s_weights_count", "s2s_create", "s2s_destroy",
            "s2s_workspace_bytes", "s2s_chunks_of_read", "s2s_forward_reads", "s2s_forward_chunks",
-           "s2s_check", "s2s_length_regulate", "s2s_digitise", "s2s_compact_reads", "s2s_profile_kernel", "s2s_launch_count"]
+           "s2s_check", "s2s_length_regulate", "s2s_digitise", "s2s_compact_reads", "s2s_profile_kernel", "s2s_launch_count", "s2s_debug_counters"]
 
 
 class S2SConfig(C.Structure):
@@ -59,7 +59,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every kernel for sm_100a into the in-tree ``libs2s_b200.so`` (nvcc cross-compiles without a GPU)."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    extra = os.environ.get("S2S_NVCC_EXTRA", "").split()
+    cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
@@ -151,6 +152,8 @@ def load() -> C.CDLL:
     lib.s2s_compact_reads.argtypes = [vp, vp, i64, i64, f32, f32, f32, i32, vp, i64, vp, vp, vp]
     lib.s2s_profile_kernel.restype = C.c_int
     lib.s2s_profile_kernel.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i64)]
+    lib.s2s_debug_counters.restype = C.c_int
+    lib.s2s_debug_counters.argtypes = [vp, i32, i32]
     if lib.s2s_abi_version() != 1:
         raise RuntimeError("libs2s_b200.so ABI version mismatch; rebuild")
     _lib = lib

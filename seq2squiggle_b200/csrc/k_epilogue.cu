@@ -55,6 +55,29 @@ __global__ void __launch_bounds__(256) k_out_epilogue(const float* __restrict__ 
   }
 }
 
+// Tensor-core path: p = ReLU(out_linear(.)) was already produced by the last FFN kernel (one float per row, 256 rows per
+// chunk); this is the x165 / noise / clamp of model.py:221-240 on 250 positions per chunk.
+__global__ void __launch_bounds__(256) k_noise_epilogue(const float* __restrict__ p_rows, const float* __restrict__ sigma_ext,
+                                                        int64_t n_pos, float scaling, s2s_run_opts o,
+                                                        float* __restrict__ p_tap, float* __restrict__ pa) {
+  const Philox ph(o.seed);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_pos; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = idx / S2S_L_DEC;
+    const int t = (int)(idx - c * S2S_L_DEC);
+    const float p = p_rows[c * S2S_L_DEC_PAD + t];
+    if (p_tap) p_tap[idx] = p;
+    float v_pa = p * scaling;
+    if (o.noise_mode != S2S_NOISE_OFF && v_pa != 0.f) {
+      const uint64_t gc = o.chunk_id_base + (uint64_t)c;
+      uint4 r = ph((uint32_t)gc, (uint32_t)(gc >> 32), (uint32_t)t, kStreamNoise);
+      float z = box_muller(r.x, r.y).x;
+      float sd = o.noise_mode == S2S_NOISE_SAMPLER ? fmaxf(sigma_ext[idx], o.min_noise) * o.noise_std * scaling : o.noise_std;
+      v_pa += z * sd;
+    }
+    pa[idx] = fmaxf(v_pa, 0.f);
+  }
+}
+
 __global__ void k_digitise(const float* __restrict__ pa, int64_t n, float dig, float range, float offset,
                            int16_t* __restrict__ raw) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -185,6 +208,17 @@ int launch_out_epilogue(const DevWeights& w, const float* y, const float* sigma_
   if (blocks > 148 * 32) blocks = 148 * 32;
   k_out_epilogue<<<(unsigned)blocks, 256, 0, st>>>(y, w.out_w, w.out_b, sigma_ext, n_pos, w.cfg.scaling_max_value, o,
                                                    p_tap, pa);
+  S2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_noise_epilogue(const DevWeights& w, const float* p_rows, const float* sigma_ext, int64_t n_chunks,
+                          const s2s_run_opts& o, float* p_tap, float* pa, cudaStream_t st) {
+  if (n_chunks == 0) return 0;
+  const int64_t n_pos = n_chunks * S2S_L_DEC;
+  int64_t blocks = ceil_div(n_pos, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_noise_epilogue<<<(unsigned)blocks, 256, 0, st>>>(p_rows, sigma_ext, n_pos, w.cfg.scaling_max_value, o, p_tap, pa);
   S2S_LAUNCH_CHECK();
   return 0;
 }

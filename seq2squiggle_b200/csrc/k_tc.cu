@@ -14,6 +14,9 @@
 // that lines up with head h inside the 32-byte Q slice of heads {2i,2i+1}; the other half is zero), so one
 // K=16 MMA computes exactly q_h . k_h.  d_v = 8 but N >= 16 for M = 128: V_h^T is padded to 16 rows with a row
 // of ones, so column 8 of O is the softmax denominator (sum of the ROUNDED probabilities) for free.
+#include <stdlib.h>
+#include <string.h>
+
 #include "s2s_tc.h"
 #include "tc_host.h"
 #include "tc_prims.cuh"
@@ -29,6 +32,22 @@ constexpr int kSlab = 128 * 128;  // bytes of one [128 rows x 128 B] tile
 // status codes written on a barrier timeout
 enum { kErrQkvLoad = 11, kErrQkvMma = 12, kErrAttLoad = 21, kErrAttS = 22, kErrAttO = 23, kErrFcLoad = 31,
        kErrFcMma = 32, kErrFfnLoad = 41, kErrFfnMma1 = 42, kErrFfnMma2 = 43 };
+
+// Optional phase timing of k_tc_attn (compile with -DS2S_PHASE_TIMING): clock64() deltas of thread 0 of every CTA,
+// summed into g_phase[] and read back through s2s_debug_counters().
+__device__ unsigned long long g_phase[16];
+#ifdef S2S_PHASE_TIMING
+// register accumulators (constant indices): a clock read + one 64-bit add per PHASE(), nothing else
+#define PHASE_DECL long long ph_acc[16]; _Pragma("unroll") for (int i_ = 0; i_ < 16; ++i_) ph_acc[i_] = 0; long long ph_t = clock64();
+#define PHASE(i) do { long long n_ = clock64(); ph_acc[i] += n_ - ph_t; ph_t = n_; } while (0)
+#define PHASE_FLUSH do { if (threadIdx.x == 0 || threadIdx.x == 128) { _Pragma("unroll") for (int i_ = 0; i_ < 16; ++i_) if (ph_acc[i_]) atomicAdd(&g_phase[i_], (unsigned long long)ph_acc[i_]); } } while (0)
+#define PHASE_COUNT(i) do { ph_acc[i] += 1; } while (0)
+#else
+#define PHASE_DECL
+#define PHASE(i) do {} while (0)
+#define PHASE_FLUSH do {} while (0)
+#define PHASE_COUNT(i) do {} while (0)
+#endif
 
 __device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, int* status, volatile int* s_abort, int code) {
   if (*s_abort) return false;
@@ -51,6 +70,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 // LayerNorm over the 64 values a thread holds for its row (biased variance, eps 1e-5), then write the
 // fp32 row (next residual) and the fp16 row (next GEMM operand).
+template <bool kStore32, bool kStore16>
 __device__ __forceinline__ void layernorm_store(float (&v)[64], const float* s_g, const float* s_b,
                                                 float* __restrict__ out32, __half* __restrict__ out16) {
   float mean = 0.f;
@@ -63,13 +83,17 @@ __device__ __forceinline__ void layernorm_store(float (&v)[64], const float* s_g
   const float rstd = 1.0f / sqrtf(var * (1.f / 64.f) + 1e-5f);
 #pragma unroll
   for (int i = 0; i < 64; ++i) v[i] = (v[i] - mean) * rstd * s_g[i] + s_b[i];
+  if (kStore32) {
 #pragma unroll
-  for (int i = 0; i < 64; i += 4)
-    *reinterpret_cast<float4*>(out32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    for (int i = 0; i < 64; i += 4)
+      *reinterpret_cast<float4*>(out32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  }
+  if (kStore16) {
 #pragma unroll
-  for (int i = 0; i < 64; i += 8)
-    *reinterpret_cast<uint4*>(out16 + i) = make_uint4(pack_half2(v[i], v[i + 1]), pack_half2(v[i + 2], v[i + 3]),
-                                                       pack_half2(v[i + 4], v[i + 5]), pack_half2(v[i + 6], v[i + 7]));
+    for (int i = 0; i < 64; i += 8)
+      *reinterpret_cast<uint4*>(out16 + i) = make_uint4(pack_half2(v[i], v[i + 1]), pack_half2(v[i + 2], v[i + 3]),
+                                                         pack_half2(v[i + 4], v[i + 5]), pack_half2(v[i + 6], v[i + 7]));
+  }
 }
 
 // =================================================================================================
@@ -155,8 +179,11 @@ __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUte
   const float kScale = 0.35355339059327373f * 1.4426950408889634f;  // log2(e) / sqrt(d_k)
   uint32_t ph_load = 0, ph_w = 0, ph_s = 0, ph_o = 0;
   int cur_g = -1;
+  PHASE_DECL
+  PHASE(9);  // prologue
   for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
     const int chunk = unit >> 1, g = unit & 1;
+    PHASE_COUNT(15);
     if (tid == 0) {
       if (g != cur_g) {  // with an even grid stride every CTA keeps its head group: loaded once
         mbar_arrive_expect_tx(&bar_w, 96 * 128);
@@ -174,6 +201,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUte
     wait_bar(&bar_load, ph_load, status, &s_abort, kErrAttLoad);
     ph_load ^= 1;
     tcgen05_fence_after();
+    PHASE(0);
     if (tid == 0) {  // [128 x 96] = X_tile Wg^T, both tiles
       const uint32_t w0 = smem_u32(sW);
 #pragma unroll
@@ -188,6 +216,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUte
     wait_bar(&bar_s, ph_s, status, &s_abort, kErrAttS);
     ph_s ^= 1;
     tcgen05_fence_after();
+    PHASE(1);
     {  // QKV epilogue: accumulators -> fp16 operands in shared memory
       uint32_t r[32];
       const float* bq = s_bias[g];
@@ -234,6 +263,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUte
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
+    PHASE(2);
 #pragma unroll 1
     for (int hh = 0; hh < 4; ++hh) {
 #pragma unroll 1
@@ -246,6 +276,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUte
         wait_bar(&bar_s, ph_s, status, &s_abort, kErrAttS);
         ph_s ^= 1;
         tcgen05_fence_after();
+        PHASE(3);
         uint32_t ra[32], rb[32];
         // pass 1: row maximum over the 250 real keys (loads double-buffered against the max3 chains)
         float m = -INFINITY;
@@ -261,6 +292,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUte
           if (c + 2 < 8) tmem_wait_ld();
         }
         const float mneg = -m * kScale;
+        PHASE(4);
         // pass 2: P = exp2(S*c - m*c) -> fp16, written over S (chunk c -> columns [16c,16c+16))
         tmem_ld_32x32(lane_addr, ra);
         tmem_wait_ld();
@@ -275,6 +307,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUte
           if (c + 2 < 8) tmem_wait_ld();
         }
         tmem_wait_st();
+        PHASE(5);
         tcgen05_fence_before();
         __syncthreads();
         if (tid == 0) {  // O = P V_h : 16 K-steps of 16 keys, A operand straight from TMEM
@@ -288,6 +321,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUte
         wait_bar(&bar_o, ph_o, status, &s_abort, kErrAttO);
         ph_o ^= 1;
         tcgen05_fence_after();
+        PHASE(6);
         uint32_t o[16];
         tmem_ld_32x16(lane_addr + 128, o);
         tmem_wait_ld();
@@ -301,12 +335,16 @@ __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUte
         tcgen05_fence_before();
         __syncthreads();  // O has been read everywhere before the next S MMA reuses the columns
         tcgen05_fence_after();
+        PHASE(7);
       }
     }
   }
+  PHASE_FLUSH;
   __syncthreads();
   if (warp == 0) tmem_dealloc<256>(tmem);
 }
+
+#include "k_tc_attn2.cuh"
 
 // =================================================================================================
 // FFN: X' = LN2(relu(Y W1^T + b1) W2^T + b2 + Y) with Y = LN1(O Wfc^T + b + X), one kernel, 128 rows per
@@ -314,7 +352,12 @@ __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUte
 // [0,128) -> D2 [128,192).  Y (fp32) stays in registers as the second residual; its fp16 copy is written
 // (swizzled) over the consumed O tile in shared memory and is the A operand of W1.
 // =================================================================================================
-template <bool kOutHead>
+// kRes32: the residual stream is fp32 in HBM (x32 read + written, x16 written) — the encoder, whose fp32 output feeds the
+//         length regulator.  Otherwise (decoder) the residual stream is the fp16 tensor x16 itself: 384 B/row of
+//         HBM traffic instead of 768.  LayerNorm, both residual adds and the accumulators stay fp32 in registers/TMEM.
+// kOutHead: last decoder block: p = ReLU(out_linear(LN2 output)) (modules.py:140-141) from the fp32 registers, one
+//         float per row; the block output itself is not written at all.
+template <bool kRes32, bool kOutHead>
 __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmWfc,
                                                       const __grid_constant__ CUtensorMap tmW1,
@@ -323,12 +366,15 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
                                                       const float* __restrict__ be1, const float* __restrict__ b1,
                                                       const float* __restrict__ b2, const float* __restrict__ g2,
                                                       const float* __restrict__ be2, float* __restrict__ x32,
-                                                      __half* __restrict__ x16, int n_tiles, int* status) {
+                                                      __half* __restrict__ x16, const float* __restrict__ w_out,
+                                                      const float* __restrict__ b_out, float* __restrict__ p_out,
+                                                      int n_tiles, int* status) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_w, bar_a[2], bar_m0, bar_m1, bar_m2;
   __shared__ uint32_t s_tmem;
   __shared__ int s_abort, s_go;
   __shared__ float s_b1[256], s_v[6][64];  // bfc, g1, be1, b2, g2, be2
+  __shared__ float s_wout[64];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* sW1 = smem;                       // [256 x 128 B]
   uint8_t* sW2 = smem + 2 * kSlab;           // 4 K-slabs x [64 x 128 B]
@@ -350,6 +396,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
   if (tid < 64) {
     s_v[0][tid] = bfc[tid]; s_v[1][tid] = g1[tid]; s_v[2][tid] = be1[tid];
     s_v[3][tid] = b2[tid]; s_v[4][tid] = g2[tid]; s_v[5][tid] = be2[tid];
+    s_wout[tid] = kOutHead ? w_out[tid] : 0.f;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -390,13 +437,26 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
     }
     const int64_t row = (int64_t)tile * 128 + tid;
     float y[64];
-    {  // first residual (the block input) while the MMA runs
+    if (kRes32) {  // first residual (the block input) while the MMA runs
       const float4* rp = reinterpret_cast<const float4*>(x32 + row * 64);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         float4 x = rp[i];
         y[4 * i] = x.x + s_v[0][4 * i]; y[4 * i + 1] = x.y + s_v[0][4 * i + 1];
         y[4 * i + 2] = x.z + s_v[0][4 * i + 2]; y[4 * i + 3] = x.w + s_v[0][4 * i + 3];
+      }
+    } else {
+      const uint4* rp = reinterpret_cast<const uint4*>(x16 + row * 64);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 x = rp[i];
+        const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[j]));
+          y[8 * i + 2 * j] = f.x + s_v[0][8 * i + 2 * j];
+          y[8 * i + 2 * j + 1] = f.y + s_v[0][8 * i + 2 * j + 1];
+        }
       }
     }
     wait_bar(&bar_m0, ph, status, &s_abort, kErrFcMma);
@@ -485,7 +545,13 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
       for (int i = 0; i < 32; ++i) y[c0 + i] += __uint_as_float(r[i]);
     }
     tcgen05_fence_before();
-    layernorm_store(y, s_v[4], s_v[5], x32 + row * 64, x16 + row * 64);
+    layernorm_store<kRes32, !kOutHead>(y, s_v[4], s_v[5], x32 + row * 64, x16 + row * 64);
+    if (kOutHead) {
+      float acc = b_out[0];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) acc = fmaf(y[i], s_wout[i], acc);
+      p_out[row] = fmaxf(acc, 0.f);
+    }
     __syncthreads();  // all TMEM reads are done before the next tile's MMA overwrites the accumulators
     tcgen05_fence_after();
   }
@@ -618,7 +684,12 @@ int tc_init(TcState& s, const DevWeights& w, int device) {
   }
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_qkv_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemQkv));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt));
-  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt));
+  if (const char* env = getenv("S2S_ATTN_V1")) s.attn_v1 = atoi(env) != 0;
+  if (const char* env = getenv("S2S_ATTN_V2")) s.attn_v1 = atoi(env) == 0;
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
   (void)w;
   S2S_CUDA_OK(cudaMalloc(&s.d_status, 256));
   S2S_CUDA_OK(cudaMemset(s.d_status, 0, 256));
@@ -630,7 +701,7 @@ void tc_destroy(TcState& s) {
   s.d_status = nullptr;
 }
 
-int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, int64_t n_chunks, cudaStream_t st) {
+int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* p_out, int64_t n_chunks, cudaStream_t st) {
   if (n_chunks == 0) return 0;
   EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(s.encode_tiled);
   const uint64_t rows = (uint64_t)n_chunks * S2S_L_DEC_PAD;
@@ -663,15 +734,22 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, 
       cudaEventCreate(&e0); cudaEventCreate(&e1);
       cudaEventRecord(e0, st);
     }
-    k_tc_attn<<<grid_att, 128, kSmemAtt, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, s.d_status);
+    if (s.attn_v1) k_tc_attn<<<grid_att, 128, kSmemAtt, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, s.d_status);
+    else k_tc_attn2<<<grid_att, kAttn2Threads, kSmemAtt, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, s.d_status);
     S2S_LAUNCH_CHECK();
     if (s.prof_on) {
       cudaEventRecord(e1, st);
       s.prof_events.push_back(e0); s.prof_events.push_back(e1);
       s.prof_chunks += n_chunks;
     }
-    k_tc_fc_ffn<false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, bl.fc_b, bl.ln1_w, bl.ln1_b, bl.b1, bl.b2,
-                                                     bl.ln2_w, bl.ln2_b, x32, b.x16, n_tiles, s.d_status);
+    if (l + 1 < w.cfg.decoder_layers)
+      k_tc_fc_ffn<false, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, bl.fc_b, bl.ln1_w, bl.ln1_b, bl.b1,
+                                                             bl.b2, bl.ln2_w, bl.ln2_b, nullptr, b.x16, nullptr, nullptr,
+                                                             nullptr, n_tiles, s.d_status);
+    else
+      k_tc_fc_ffn<false, true><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, bl.fc_b, bl.ln1_w, bl.ln1_b, bl.b1,
+                                                            bl.b2, bl.ln2_w, bl.ln2_b, nullptr, b.x16, w.out_w, w.out_b,
+                                                            p_out, n_tiles, s.d_status);
     S2S_LAUNCH_CHECK();
   }
   return 0;
@@ -710,8 +788,9 @@ int tc_encoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, 
     k_tc_qkv_plain<<<grid2, 128, kSmemQkv, st>>>(tmX, tmWqkv, bl.bqkv, qkv32, (int64_t)rows, s.d_status);
     S2S_LAUNCH_CHECK();
     if (launch_attention_enc_f16out(qkv32, o16, n_chunks, st)) return -1;
-    k_tc_fc_ffn<false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, bl.fc_b, bl.ln1_w, bl.ln1_b, bl.b1, bl.b2,
-                                                     bl.ln2_w, bl.ln2_b, x32, x16, n_tiles, s.d_status);
+    k_tc_fc_ffn<true, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, bl.fc_b, bl.ln1_w, bl.ln1_b, bl.b1, bl.b2,
+                                                           bl.ln2_w, bl.ln2_b, x32, x16, nullptr, nullptr, nullptr, n_tiles,
+                                                           s.d_status);
     S2S_LAUNCH_CHECK();
   }
   (void)b;
@@ -738,6 +817,18 @@ int tc_profile(TcState& s, int enable, double* ms_total, int64_t* launches, int6
   if (launches) *launches = (int64_t)(s.prof_events.size() / 2);
   if (chunks) *chunks = s.prof_chunks;
   s.prof_events.clear();
+  return 0;
+}
+
+int tc_debug_counters(int64_t* out, int n, int reset) {
+  unsigned long long h[16];
+  S2S_CUDA_OK(cudaDeviceSynchronize());
+  S2S_CUDA_OK(cudaMemcpyFromSymbol(h, g_phase, sizeof h));
+  for (int i = 0; i < n && i < 16; ++i) out[i] = (int64_t)h[i];
+  if (reset) {
+    memset(h, 0, sizeof h);
+    S2S_CUDA_OK(cudaMemcpyToSymbol(g_phase, h, sizeof h));
+  }
   return 0;
 }
 

@@ -155,7 +155,7 @@ struct Workspace {
   // per sub-batch
   float *emb, *xe, *qkv_e, *att_e, *ye, *he, *h3, *sigma;
   int32_t *dur, *total;
-  float *xd, *qkv_d, *att_d, *yd, *hd, *sigma_ext;
+  float *xd, *qkv_d, *att_d, *yd, *hd, *sigma_ext, *p_rows;
   TcBuffers tcb;
 };
 
@@ -185,6 +185,7 @@ int64_t carve(Workspace& w, void* base, const s2s_engine* h, int64_t n_chunks, i
   w.yd = cv.take<float>(md * 64);
   w.hd = cv.take<float>(md * 256);
   w.sigma_ext = cv.take<float>(bc * S2S_L_DEC);
+  w.p_rows = cv.take<float>(md);
   tc_carve(w.tcb, cv.base, cv.off, bc);
   (void)n_reads;
   return cv.off;
@@ -236,7 +237,8 @@ int run_pipeline(s2s_engine* h, const uint8_t* bases, const int8_t* codes, const
                              taps && taps->rate_dev ? taps->rate_dev + c0 * 16 : nullptr,
                              taps && taps->dur_float_dev ? taps->dur_float_dev + c0 * 16 : nullptr, st)) return -1;
     // K-D
-    if (launch_length_regulate(w.xe, w.sigma, w.dur, bc, dw.dec_pos, w.xd, tc_path ? w.tcb.x16 : nullptr, S2S_L_DEC_PAD,
+    // fp32 path: fp32 residual stream xd; tensor-core path: the fp16 stream x16 is the only copy
+    if (launch_length_regulate(w.xe, w.sigma, w.dur, bc, dw.dec_pos, tc_path ? nullptr : w.xd, tc_path ? w.tcb.x16 : nullptr, S2S_L_DEC_PAD,
                                w.sigma_ext, w.total,
                                taps && taps->lr_out_dev ? taps->lr_out_dev + c0 * S2S_L_DEC * 64 : nullptr, st)) return -1;
     if (taps) {
@@ -252,12 +254,16 @@ int run_pipeline(s2s_engine* h, const uint8_t* bases, const int8_t* codes, const
       for (int l = 0; l < h->cfg.decoder_layers; ++l)
         if (fft_block_f32(dw.dec[l], w.xd, w.yd, w.qkv_d, w.att_d, w.hd, bc, S2S_L_DEC, S2S_L_DEC_PAD, st)) return -1;
     } else {
-      if (tc_decoder(h->tc, dw, w.tcb, w.xd, bc, st)) return -1;
+      if (tc_decoder(h->tc, dw, w.tcb, w.p_rows, bc, st)) return -1;
     }
     // K-F
     float* pa_b = pa_out + c0 * S2S_L_DEC;
-    if (launch_out_epilogue(dw, w.xd, w.sigma_ext, bc, o, taps && taps->p_dev ? taps->p_dev + c0 * S2S_L_DEC : nullptr,
-                            pa_b, st)) return -1;
+    float* p_tap = taps && taps->p_dev ? taps->p_dev + c0 * S2S_L_DEC : nullptr;
+    if (tc_path) {
+      if (launch_noise_epilogue(dw, w.p_rows, w.sigma_ext, bc, o, p_tap, pa_b, st)) return -1;
+    } else if (launch_out_epilogue(dw, w.xd, w.sigma_ext, bc, o, p_tap, pa_b, st)) {
+      return -1;
+    }
     if (taps && tap_copy(taps->pa_dev ? taps->pa_dev + c0 * S2S_L_DEC : nullptr, pa_b, bc * S2S_L_DEC * 4, st)) return -1;
   }
   return 0;
@@ -441,6 +447,11 @@ int s2s_check(s2s_handle h, s2s_stream stream) {
 int s2s_profile_kernel(s2s_handle h, int enable, double* ms_total, int64_t* launches, int64_t* chunks) {
   if (!h) { set_error("null handle"); return -1; }
   return tc_profile(h->tc, enable, ms_total, launches, chunks);
+}
+
+int s2s_debug_counters(int64_t* out, int32_t n, int32_t reset) {
+  if (!out || n < 0) { set_error("bad arguments"); return -1; }
+  return tc_debug_counters(out, n, reset);
 }
 
 int s2s_length_regulate(const float* x_dev, const float* sigma_dev, const int32_t* dur_dev, int64_t n_chunks,

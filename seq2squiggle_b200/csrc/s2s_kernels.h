@@ -70,6 +70,9 @@ int launch_length_regulate(const float* enc_out, const float* sigma, const int32
 // p = ReLU(y . w_out + b); pA = clamp(165 p + noise, 0).  y has 256 rows per chunk, outputs 250 per chunk.
 int launch_out_epilogue(const DevWeights& w, const float* y, const float* sigma_ext, int64_t n_chunks,
                         const s2s_run_opts& o, float* p_tap, float* pa, cudaStream_t st);
+// same, for p already computed per row (256 rows per chunk) by the last tensor-core FFN kernel
+int launch_noise_epilogue(const DevWeights& w, const float* p_rows, const float* sigma_ext, int64_t n_chunks,
+                          const s2s_run_opts& o, float* p_tap, float* pa, cudaStream_t st);
 int launch_digitise(const float* pa, int64_t n, float dig, float range, float offset, int16_t* raw, cudaStream_t st);
 int64_t compact_workspace_bytes(int64_t n_chunks);
 int launch_compact(const float* pa, const int64_t* chunk_offsets, int64_t n_reads, int64_t n_chunks, float dig,

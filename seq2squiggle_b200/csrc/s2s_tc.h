@@ -12,6 +12,7 @@ struct TcState {
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled entry point
   int32_t* d_status = nullptr;   // device word set by a kernel whose mbarrier wait timed out
   // optional CUDA-event bracketing of the attention launches (bench.py roofline leg)
+  bool attn_v1 = true;           // S2S_ATTN_V1=1: the unpipelined attention kernel (A/B measurements)
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_events;   // start/stop pairs
   int64_t prof_chunks = 0;
@@ -30,11 +31,15 @@ int tc_init(TcState& s, const DevWeights& w, int device);
 void tc_destroy(TcState& s);
 // Runs all decoder layers in place on x32 ([chunks*256,64] fp32 residual stream).
 int tc_profile(TcState& s, int enable, double* ms_total, int64_t* launches, int64_t* chunks);
+// Phase-timing counters of k_tc_attn (all zero unless built with -DS2S_PHASE_TIMING).
+int tc_debug_counters(int64_t* out, int n, int reset);
 // Synchronises the stream and reports a device-side barrier timeout, if any.
 int tc_check_status(TcState& s, cudaStream_t st);
+// Runs all decoder layers on the fp16 residual stream b.x16 ([chunks*256,64], written by the length regulator) and
+// writes p = ReLU(out_linear(.)) for every row to p_out [chunks*256].
+int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* p_out, int64_t n_chunks, cudaStream_t st);
 // Runs all encoder layers in place on x32/x16 ([chunks*16 rows, padded to 128]); qkv32 [rows,192], o16 [rows,64] scratch.
 int tc_encoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, __half* x16, float* qkv32, __half* o16,
                int64_t n_chunks, cudaStream_t st);
-int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, int64_t n_chunks, cudaStream_t st);
 
 }  // namespace s2s
