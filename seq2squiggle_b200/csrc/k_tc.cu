@@ -138,7 +138,14 @@ __device__ __forceinline__ void chunk_exp_store(const uint32_t (&r)[32], float s
 __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUtensorMap tmX,
                                                     const __grid_constant__ CUtensorMap tmWg,
                                                     const float* __restrict__ bias_g, __half* __restrict__ o16,
-                                                    int n_units, int* status) {
+                                                    int n_units, const int* __restrict__ unit_flags,
+                                                    const int* __restrict__ n_flagged, int* status) {
+  // As the exact fallback of k_tc_attn2 (unit_flags != nullptr) only the flagged units are recomputed.
+  if (unit_flags) {
+    const int nf = *n_flagged;
+    if (nf == 0) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_phase[12], (unsigned long long)nf);
+  }
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_load, bar_w, bar_s, bar_o;
   __shared__ uint32_t s_tmem;
@@ -182,6 +189,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUte
   PHASE_DECL
   PHASE(9);  // prologue
   for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    if (unit_flags && !unit_flags[unit]) continue;
     const int chunk = unit >> 1, g = unit & 1;
     PHASE_COUNT(15);
     if (tid == 0) {
@@ -670,6 +678,7 @@ void tc_carve(TcBuffers& b, char* base, int64_t& off, int64_t bc) {
   const int64_t erows = align_up(bc * S2S_L_ENC, 128);
   b.xe16 = reinterpret_cast<__half*>(take(erows * 64 * 2));
   b.oe16 = reinterpret_cast<__half*>(take(erows * 64 * 2));
+  b.flags = reinterpret_cast<int32_t*>(take((2 * bc + 1) * 4));
 }
 
 int tc_init(TcState& s, const DevWeights& w, int device) {
@@ -684,7 +693,7 @@ int tc_init(TcState& s, const DevWeights& w, int device) {
   }
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_qkv_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemQkv));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt));
-  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt));
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn2, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
   if (const char* env = getenv("S2S_ATTN_V1")) s.attn_v1 = atoi(env) != 0;
   if (const char* env = getenv("S2S_ATTN_V2")) s.attn_v1 = atoi(env) == 0;
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
@@ -717,6 +726,7 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* p_out
   }
   const int grid2 = n_tiles < 2 * s.sm_count ? n_tiles : 2 * s.sm_count;
   const int n_units = (int)(2 * n_chunks);
+  int32_t* d_flags = b.flags;  // [0] = number of flagged units, [1..] = per-unit overflow flags (workspace)
   const int grid_att = n_units < 2 * s.sm_count ? n_units : 2 * s.sm_count;  // even stride: a CTA keeps its head group
   for (int l = 0; l < w.cfg.decoder_layers; ++l) {
     const BlockDev& bl = w.dec[l];
@@ -734,8 +744,19 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* p_out
       cudaEventCreate(&e0); cudaEventCreate(&e1);
       cudaEventRecord(e0, st);
     }
-    if (s.attn_v1) k_tc_attn<<<grid_att, 128, kSmemAtt, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, s.d_status);
-    else k_tc_attn2<<<grid_att, kAttn2Threads, kSmemAtt, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, s.d_status);
+    if (s.attn_v1) {
+      k_tc_attn<<<grid_att, 128, kSmemAtt, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, nullptr, nullptr, s.d_status);
+    } else {
+      // fast kernel (one reference max per row) + exact recomputation of the units whose fp16 P overflowed
+      S2S_CUDA_OK(cudaMemsetAsync(d_flags, 0, (size_t)(n_units + 1) * sizeof(int), st));
+      static const bool one_cta = getenv("S2S_ATTN_1CTA") && atoi(getenv("S2S_ATTN_1CTA"));
+      const int grid2a = one_cta ? (n_units < s.sm_count ? n_units : s.sm_count) : grid_att;
+      const int smem2a = one_cta ? 150 * 1024 : kSmemAtt;
+      k_tc_attn2<<<grid2a, kAttn2Threads, smem2a, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags,
+                                                           s.d_status);
+      S2S_LAUNCH_CHECK();
+      k_tc_attn<<<grid_att, 128, kSmemAtt, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags, s.d_status);
+    }
     S2S_LAUNCH_CHECK();
     if (s.prof_on) {
       cudaEventRecord(e1, st);

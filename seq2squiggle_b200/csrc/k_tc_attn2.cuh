@@ -1,20 +1,24 @@
 // k_tc_attn2 — pipelined decoder attention (included by k_tc.cu inside namespace s2s::{anonymous}).
 //
-// Same math and operand layouts as k_tc_attn (fused QKV projection, masked K, padded V^T with a ones row, fp16
-// P in TMEM, TS-mode P.V), restructured so the MUFU pipe never waits for a tensor-core round trip:
+// Same operand layouts as k_tc_attn (fused QKV projection, masked K, padded V^T with a ones row, fp16 P in TMEM,
+// TS-mode P.V), restructured so that a softmax warp does almost nothing but exponentials:
 //   * 5 warps: warps 0-3 are the softmax warps (one query row per thread, TMEM lanes 32w..32w+31); warp 4 issues every
-//     TMA load and tcgen05.mma and only talks to the others through mbarriers — there is no __syncthreads in the
-//     steady state, so warps drift freely and the four schedulers always have an exp-ready warp;
-//   * the 250 keys of a (head, query tile) are processed as FOUR 64-key quarters with a flash-style running
-//     max / rescale, so a quarter's scores need only 64 TMEM columns: the CTA's 256 columns are a ring of four
-//     buffers [S_q | P_q over S_q | O_q at +32].  S(j+2) and P.V(j) run on the tensor pipe while the softmax warps
-//     are busy with quarter j+1, i.e. MMA latency (~500 clk) is fully hidden;
-//   * a quarter's 64 scores stay in registers between the max and the exp (one tcgen05.ld per score instead of two).
-// Micro-iteration j = ((hh*2 + tile)*4 + q) uses ring buffer q.  Barriers (each completes once per (hh,tile)):
-//   bar_S[q]  MMA warp  -> softmax : S_q ready          (tcgen05.commit)
-//   bar_P[q]  softmax   -> MMA warp: P_q written        (4 warp arrivals)
-//   bar_O[q]  MMA warp  -> softmax : O_q = P_q V ready  (tcgen05.commit)
-//   bar_F[q]  softmax   -> MMA warp: O_q read, buffer q free (4 warp arrivals)
+//     TMA load and tcgen05.mma and talks to the others only through mbarriers — no __syncthreads in the steady state;
+//   * the 250 keys of a (head, query tile) are processed as four 64-key quarters whose scores live in a ring of
+//     three 64-column TMEM buffers [S_q, overwritten by P_q]; S(j+2) and P.V(j) run on the tensor pipe while the
+//     softmax warps work on quarter j+1, so no MMA round trip (~500 clk) is ever waited for;
+//   * ONE reference maximum per row: m_ref = max of the row's first 32 scores.  Softmax is invariant to the reference,
+//     m_ref <= the true maximum so the largest probability is >= 1 (nothing underflows), and P = exp2((s - m_ref) c)
+//     only misbehaves if it overflows fp16 (s - m_ref > ~31).  Then the row's denominator — accumulated by the
+//     tensor core from the same fp16 P through the ones row of V^T — is inf/NaN: the unit is flagged and recomputed
+//     by the exact two-pass kernel k_tc_attn.  With a fixed reference all four quarters accumulate into one TMEM
+//     accumulator (no per-quarter rescale, no max pass, one tcgen05.ld per score instead of two);
+//   * two O accumulators (columns 192.. and 208..) alternate between consecutive (head, tile)s; O is read one quarter
+//     after its last P.V was issued.
+// Ring barriers complete once per use of a buffer (parity = use count & 1, tracked identically by both roles):
+//   bar_S[b]  MMA warp -> softmax : S ready (tcgen05.commit)     bar_P[b]  softmax -> MMA warp: P written (4 warps)
+//   bar_PV[b] MMA warp -> both    : P.V of that buffer done -> buffer reusable; for a row's last quarter: O ready
+//   bar_OF[a] softmax  -> MMA warp: accumulator a has been read (4 warps)
 #pragma once
 
 constexpr int kAttn2Threads = 160;
@@ -24,21 +28,25 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar) {
   if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
 
-// acc (8 dims + rowsum) <- acc * 2^((m_run - m_new) c) + o * 2^((m_q - m_new) c)
-__device__ __forceinline__ void online_combine(float (&acc)[9], float& m_run, const uint32_t (&o)[16], float m_q, float c) {
-  const float m_new = fmaxf(m_run, m_q);
-  const float a = ex2_approx((m_run - m_new) * c), b = ex2_approx((m_q - m_new) * c);
-#pragma unroll
-  for (int i = 0; i < 9; ++i) acc[i] = fmaf(acc[i], a, __uint_as_float(o[i]) * b);
-  m_run = m_new;
-}
+struct Ring3 {  // which of the three S/P buffers the next quarter uses, and the parity of that use
+  uint32_t b = 0, bits = 0;
+  __device__ __forceinline__ void next(uint32_t& ob, uint32_t& opar) {
+    ob = b;
+    opar = (bits >> b) & 1u;
+    bits ^= 1u << b;
+    b = (b == 2u) ? 0u : b + 1u;
+  }
+};
 
 __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_constant__ CUtensorMap tmX,
                                                                const __grid_constant__ CUtensorMap tmWg,
                                                                const float* __restrict__ bias_g, __half* __restrict__ o16,
-                                                               int n_units, int* status) {
+                                                               int n_units, int* __restrict__ unit_flags,
+                                                               int* __restrict__ n_flagged, int* status) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_load, bar_w, bar_qkv, bar_kv, bar_unit, bar_S[4], bar_P[4], bar_O[4], bar_F[4];
+  // all barriers in one array: a barrier is addressed as (32-bit shared address of bars) + 8 * index
+  enum { B_LOAD = 0, B_W, B_QKV, B_KV, B_UNIT, B_S, B_P = B_S + 3, B_PV = B_P + 3, B_OF = B_PV + 3, B_COUNT = B_OF + 2 };
+  __shared__ __align__(8) uint64_t bars[B_COUNT];
   __shared__ uint32_t s_tmem;
   __shared__ int s_abort, s_go;
   __shared__ float s_bias[2][96];
@@ -53,15 +61,20 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
   if (!s_go) return;
   if (warp == 0) tmem_alloc<256>(&s_tmem);
   if (tid == 0) {
-    mbar_init(&bar_load, 1); mbar_init(&bar_w, 1); mbar_init(&bar_qkv, 1); mbar_init(&bar_kv, 4); mbar_init(&bar_unit, 4);
-    for (int q = 0; q < 4; ++q) { mbar_init(&bar_S[q], 1); mbar_init(&bar_O[q], 1); mbar_init(&bar_P[q], 4); mbar_init(&bar_F[q], 4); }
+    mbar_init(&bars[B_LOAD], 1); mbar_init(&bars[B_W], 1); mbar_init(&bars[B_QKV], 1); mbar_init(&bars[B_KV], 4);
+    mbar_init(&bars[B_UNIT], 4);
+    for (int b = 0; b < 3; ++b) { mbar_init(&bars[B_S + b], 1); mbar_init(&bars[B_PV + b], 1); mbar_init(&bars[B_P + b], 4); }
+    mbar_init(&bars[B_OF], 4); mbar_init(&bars[B_OF + 1], 4);
     fence_mbar_init();
     s_abort = 0;
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmWg);
   }
   for (int i = tid; i < 192; i += kAttn2Threads) s_bias[i / 96][i % 96] = bias_g[i];
   // V^T padding rows are constant: row 8 of every head = ones (softmax denominator), rows 9..15 = 0
-  for (int i = tid; i < 2 * kSlab / 16; i += kAttn2Threads) reinterpret_cast<uint4*>(sV)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < 2 * kSlab / 16; i += kAttn2Threads) {
+    reinterpret_cast<uint4*>(sV)[i] = make_uint4(0u, 0u, 0u, 0u);
+    reinterpret_cast<uint4*>(sK)[i] = make_uint4(0u, 0u, 0u, 0u);  // the masked (zero) half of every K slot never changes
+  }
   __syncthreads();
   for (int i = tid; i < 4 * 4 * 8; i += kAttn2Threads) {  // (quarter, head, 16-byte chunk of 8 keys)
     const int slab = i >> 5, hh = (i >> 3) & 3, ck = i & 7;
@@ -73,7 +86,25 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = s_tmem;
+  const uint32_t bar0 = smem_u32(&bars[0]), abort_a = smem_u32(&s_abort);
+  auto BAR = [&](uint32_t idx) { return bar0 + 8u * idx; };
+  // bounded wait on a barrier address; the abort flag is only consulted on the slow path
+  auto wait_a = [&](uint32_t a, uint32_t parity, int code) -> bool {
+    for (uint32_t i = 0; i < kWaitLimit; ++i) {
+      if (mbar_try_wait_a(a, parity)) return true;
+      if ((i & 255u) == 255u && lds_u32(abort_a)) return false;
+    }
+    sts_u32(abort_a, 1u);
+    atomicExch(status, code);
+    return false;
+  };
+  auto warp_arrive_a = [&](uint32_t a) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive_a(a);
+  };
   const float kScale = 0.35355339059327373f * 1.4426950408889634f;  // log2(e) / sqrt(d_k)
+  constexpr uint32_t kOaccCol = 192;
+  Ring3 ring;
   PHASE_DECL
 
   if (warp == 4) {
@@ -82,218 +113,222 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
                    idesc_o = umma_idesc(128, 16, kFmtF16);
     const uint32_t aXQ = smem_u32(sXQ), aW = smem_u32(sW);
     const uint64_t dXQ = umma_desc_k_sw128(aXQ), dK = umma_desc_k_sw128(smem_u32(sK)), dV = umma_desc_k_sw128(smem_u32(sV));
-    const bool elected = lane == 0;
-    uint32_t mg0 = 0, it = 0, ph_w = 0;
+    uint32_t it = 0, ph_w = 0;
     int cur_g = -1;
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it, mg0 += 8) {
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
       const int chunk = unit >> 1, g = unit & 1;
       const uint32_t upar = it & 1;
-      if (elected) {
+      if (elect_one()) {
         if (g != cur_g) {  // with an even grid stride every CTA keeps its head group: loaded once
-          mbar_arrive_expect_tx(&bar_w, 96 * 128);
-          tma_load_2d(sW, &tmWg, &bar_w, 0, g * 96);
+          mbar_arrive_expect_tx(&bars[B_W], 96 * 128);
+          tma_load_2d(sW, &tmWg, &bars[B_W], 0, g * 96);
         }
-        mbar_arrive_expect_tx(&bar_load, 2 * kSlab);
-        tma_load_2d(sXQ, &tmX, &bar_load, 0, chunk * 256);
-        tma_load_2d(sXQ + kSlab, &tmX, &bar_load, 0, chunk * 256 + 128);
+        mbar_arrive_expect_tx(&bars[B_LOAD], 2 * kSlab);
+        tma_load_2d(sXQ, &tmX, &bars[B_LOAD], 0, chunk * 256);
+        tma_load_2d(sXQ + kSlab, &tmX, &bars[B_LOAD], 0, chunk * 256 + 128);
       }
       if (g != cur_g) {
-        wait_bar(&bar_w, ph_w, status, &s_abort, kErrAttLoad);
+        wait_a(BAR(B_W), ph_w, kErrAttLoad);
         ph_w ^= 1;
         cur_g = g;
       }
-      wait_bar(&bar_load, upar, status, &s_abort, kErrAttLoad);
+      wait_a(BAR(B_LOAD), upar, kErrAttLoad);
       tcgen05_fence_after();
-      if (elected) {  // [128 x 96] = X_tile Wg^T, both tiles (accumulators at columns 0 and 128)
+      if (elect_one()) {  // [128 x 96] = X_tile Wg^T, both tiles (accumulators at columns 0 and 128)
 #pragma unroll
         for (int tile = 0; tile < 2; ++tile)
 #pragma unroll
           for (int s = 0; s < 4; ++s)
             umma_f16_ss(tmem + tile * 128, umma_desc_k_sw128(aXQ + tile * kSlab + s * 32), umma_desc_k_sw128(aW + s * 32),
                         idesc_qkv, s > 0);
-        umma_commit(&bar_qkv);
+        umma_commit_a(BAR(B_QKV));
       }
-      wait_bar(&bar_kv, upar, status, &s_abort, kErrAttS);  // Q / K / V^T operands are in shared memory
+      wait_a(BAR(B_KV), upar, kErrAttS);  // Q / K / V^T operands are in shared memory
       tcgen05_fence_after();
-      // Descriptors are base + (byte offset >> 4) with compile-time offsets inside the unrolled quarter loop, so an
-      // MMA costs one or two uniform-datapath adds to issue (the issue warp must cycle faster than a softmax quarter).
-      if (elected) {
-        umma_f16_ss(tmem, dXQ, dK, idesc_s, 0);                       // S(M=0, q=0)
-        umma_commit(&bar_S[0]);
-        umma_f16_ss(tmem + 64, dXQ, dK + (8192 >> 4), idesc_s, 0);    // S(M=0, q=1)
-        umma_commit(&bar_S[1]);
+      // S for quarter j: A = Q slice of (tile, head pair), B = masked-K slot of the head, rows of key quarter q
+      auto issue_S = [&](int j, uint32_t buf) {
+        const int M = j >> 2, q = j & 3, hh = M >> 1, tile = M & 1;
+        umma_f16_ss(tmem + 64 * buf, dXQ + (uint64_t)((tile * kSlab + (hh >> 1) * 32) >> 4),
+                    dK + (uint64_t)((q * 8192 + hh * 32) >> 4), idesc_s, 0);
+        umma_commit_a(BAR(B_S + buf));
+      };
+      {  // all three ring buffers are free at the start of a unit: S of quarters 0, 1, 2
+        const uint32_t b0 = ring.b, b1 = (b0 == 2u) ? 0u : b0 + 1u, b2 = (b1 == 2u) ? 0u : b1 + 1u;
+        if (elect_one()) { issue_S(0, b0); issue_S(1, b1); issue_S(2, b2); }
       }
 #pragma unroll 1
-      for (int M = 0; M < 8; ++M) {
-        const int hh = M >> 1, tile = M & 1, Mn = M + 1;
-        const uint32_t par = (mg0 + M) & 1;
-        const uint64_t dA = dXQ + (uint64_t)((tile * kSlab + (hh >> 1) * 32) >> 4);             // Q slice of (tile, head pair)
-        const uint64_t dB = dK + (uint64_t)((hh * 32) >> 4);                                     // masked K slot of head hh
-        const uint64_t dAn = dXQ + (uint64_t)(((Mn & 1) * kSlab + ((Mn >> 1) >> 1) * 32) >> 4);  // same for (M+1)
-        const uint64_t dBn = dK + (uint64_t)(((Mn >> 1) * 32) >> 4);
-        const uint64_t dVh = dV + (uint64_t)((hh * 2048) >> 4);                                  // V^T rows of head hh
+      for (int j = 0; j < 32; ++j) {
+        const int M = j >> 2, q = j & 3, hh = M >> 1, acc_i = M & 1;
+        uint32_t b, par;
+        ring.next(b, par);
+        if (q == 0 && (it > 0 || M >= 2)) {  // accumulator acc_i still holds the O of two (head, tile)s ago until it is read
+          const uint32_t use = 4u * it + (uint32_t)(M >> 1);
+          wait_a(BAR(B_OF + acc_i), (use - 1u) & 1u, kErrAttO);
+        }
+        wait_a(BAR(B_P + b), par, kErrAttO);
+        tcgen05_fence_after();
+        PHASE(10);
+        if (elect_one()) {  // O += P_q V_h over the quarter's 64 keys: 4 K-steps, A operand straight from TMEM
+          const uint64_t dVq = dV + (uint64_t)((q * 8192 + hh * 2048) >> 4);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          wait_bar(&bar_P[q], par, status, &s_abort, kErrAttO);
+          for (int ks = 0; ks < 4; ++ks)
+            umma_f16_ts(tmem + kOaccCol + 16 * acc_i, tmem + 64 * b + 8 * ks, dVq + (uint64_t)((ks * 32) >> 4), idesc_o,
+                        (q > 0 || ks > 0) ? 1u : 0u);
+          umma_commit_a(BAR(B_PV + b));
+        }
+        PHASE(11);
+        if (j + 3 < 32) {  // this buffer is free again as soon as its P.V has completed: S three quarters ahead goes in
+          wait_a(BAR(B_PV + b), par, kErrAttS);
           tcgen05_fence_after();
-          PHASE(10);
-          if (elected) {  // O_q = P_q V_h over the quarter's 64 keys: 4 K-steps, A operand straight from TMEM
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_f16_ts(tmem + 64 * q + 32, tmem + 64 * q + 8 * ks, dVh + (uint64_t)((q * 8192 + ks * 32) >> 4), idesc_o, ks > 0);
-            umma_commit(&bar_O[q]);
-          }
-          PHASE(11);
-          // S two quarters ahead goes into ring buffer (q+2)&3, last used two quarters ago: its O must have been read
-          const int q2 = (q + 2) & 3;
-          if (q < 2) {
-            if (M > 0) {
-              wait_bar(&bar_F[q2], par ^ 1, status, &s_abort, kErrAttS);
-              tcgen05_fence_after();
-            }
-            PHASE(12);
-            if (elected) {
-              umma_f16_ss(tmem + 64 * q2, dA, dB + (uint64_t)((q2 * 8192) >> 4), idesc_s, 0);
-              umma_commit(&bar_S[q2]);
-            }
-          } else if (M < 7) {
-            wait_bar(&bar_F[q2], par, status, &s_abort, kErrAttS);
-            tcgen05_fence_after();
-            PHASE(12);
-            if (elected) {
-              umma_f16_ss(tmem + 64 * q2, dAn, dBn + (uint64_t)((q2 * 8192) >> 4), idesc_s, 0);
-              umma_commit(&bar_S[q2]);
-            }
-          }
+          PHASE(12);
+          if (elect_one()) issue_S(j + 3, b);
           PHASE(13);
         }
       }
-      // every softmax warp has drained its last O: shared-memory operands and TMEM may be overwritten
-      wait_bar(&bar_unit, upar, status, &s_abort, kErrAttO);
+      // every softmax warp has read its last O: shared-memory operands and TMEM may be overwritten
+      wait_a(BAR(B_UNIT), upar, kErrAttO);
       tcgen05_fence_after();
     }
   } else {
     // =============================== softmax warps ===============================================
     const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
-    uint32_t mg = 0, it = 0;
+    uint32_t it = 0;
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
       const int chunk = unit >> 1, g = unit & 1;
       const uint32_t upar = it & 1;
       PHASE_COUNT(15);
-      wait_bar(&bar_qkv, upar, status, &s_abort, kErrAttS);
+      wait_a(BAR(B_QKV), upar, kErrAttS);
       tcgen05_fence_after();
       PHASE(1);
-      {  // QKV epilogue: accumulators -> fp16 operands in shared memory
-        uint32_t r[32];
+      {  // QKV epilogue: accumulators -> fp16 operands in shared memory.  Only Q needs its bias here: the K bias adds a
+         // per-row constant q.b_k to every score (softmax-invariant), and the V bias is added once to the normalised
+         // output (sum_j p_j (v_j + b_v) = sum_j p_j v_j + b_v).  The zero halves of the masked K slots are static.
         const float* bq = s_bias[g];
 #pragma unroll
         for (int tile = 0; tile < 2; ++tile) {
           const int t = tile * 128 + tid;  // key / query index inside the chunk
-          tmem_ld_32x32(lane_addr + tile * 128, r);
+          uint32_t rq[32], rk[32], rv[32];
+          tmem_ld_32x32(lane_addr + tile * 128, rq);
+          tmem_ld_32x32(lane_addr + tile * 128 + 32, rk);
+          tmem_ld_32x32(lane_addr + tile * 128 + 64, rv);
           tmem_wait_ld();
 #pragma unroll
           for (int hh = 0; hh < 4; ++hh) {
-            uint32_t pk[4];
+            uint32_t pq[4], pk[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              pk[i] = pack_half2(__uint_as_float(r[8 * hh + 2 * i]) + bq[8 * hh + 2 * i],
-                                 __uint_as_float(r[8 * hh + 2 * i + 1]) + bq[8 * hh + 2 * i + 1]);
-            *reinterpret_cast<uint4*>(sXQ + tile * kSlab + sw128_offset(tid, hh)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            for (int i = 0; i < 4; ++i) {
+              pq[i] = pack_half2(__uint_as_float(rq[8 * hh + 2 * i]) + bq[8 * hh + 2 * i],
+                                 __uint_as_float(rq[8 * hh + 2 * i + 1]) + bq[8 * hh + 2 * i + 1]);
+              pk[i] = pack_half2(__uint_as_float(rk[8 * hh + 2 * i]), __uint_as_float(rk[8 * hh + 2 * i + 1]));
+            }
+            *reinterpret_cast<uint4*>(sXQ + tile * kSlab + sw128_offset(tid, hh)) = make_uint4(pq[0], pq[1], pq[2], pq[3]);
+            *reinterpret_cast<uint4*>(sK + sw128_offset(t, 2 * hh + (hh & 1))) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
-          tmem_ld_32x32(lane_addr + tile * 128 + 32, r);
-          tmem_wait_ld();
-#pragma unroll
-          for (int hh = 0; hh < 4; ++hh) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              pk[i] = pack_half2(__uint_as_float(r[8 * hh + 2 * i]) + bq[32 + 8 * hh + 2 * i],
-                                 __uint_as_float(r[8 * hh + 2 * i + 1]) + bq[32 + 8 * hh + 2 * i + 1]);
-            const uint4 data = make_uint4(pk[0], pk[1], pk[2], pk[3]), zero = make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(sK + sw128_offset(t, 2 * hh)) = (hh & 1) ? zero : data;
-            *reinterpret_cast<uint4*>(sK + sw128_offset(t, 2 * hh + 1)) = (hh & 1) ? data : zero;
-          }
-          tmem_ld_32x32(lane_addr + tile * 128 + 64, r);
-          tmem_wait_ld();
           uint8_t* vslab = sV + (t >> 6) * 8192 + (t & 7) * 2;
           const uint32_t ck = (t & 63) >> 3;
 #pragma unroll
           for (int hh = 0; hh < 4; ++hh)
 #pragma unroll
             for (int d = 0; d < 8; ++d)
-              *reinterpret_cast<__half*>(vslab + sw128_offset(hh * 16 + d, ck)) =
-                  __float2half_rn(__uint_as_float(r[8 * hh + d]) + bq[64 + 8 * hh + d]);
+              *reinterpret_cast<__half*>(vslab + sw128_offset(hh * 16 + d, ck)) = __float2half_rn(__uint_as_float(rv[8 * hh + d]));
         }
       }
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
       tcgen05_fence_before();
-      warp_arrive(&bar_kv);
+      warp_arrive_a(BAR(B_KV));
       PHASE(2);
 
-      float acc[9], m_run = -INFINITY, mq[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int i = 0; i < 9; ++i) acc[i] = 0.f;
-      auto take_O = [&](int b, uint32_t parity, float m_b) {
-        wait_bar(&bar_O[b], parity, status, &s_abort, kErrAttO);
+      bool overflow = false;
+      uint32_t ob = 0, opar = 0;  // ring slot of the pending row's last quarter: its bar_PV is "O ready"
+      uint32_t o[16];
+      // O of (head, tile) M: wait for its last P.V, start the TMEM read ...
+      auto take_O_issue = [&]() {
+        wait_a(BAR(B_PV + ob), opar, kErrAttO);
         tcgen05_fence_after();
-        uint32_t o[16];
-        tmem_ld_32x16(lane_addr + 64 * b + 32, o);
-        tmem_wait_ld();
+      };
+      // ... and, once a tcgen05.wait::ld has covered it, release the accumulator, normalise, add the V bias, store.
+      auto take_O_finish = [&](int M) {
+        const int hh = M >> 1, tile = M & 1, acc_i = M & 1;
         tcgen05_fence_before();
-        warp_arrive(&bar_F[b]);
-        online_combine(acc, m_run, o, m_b, kScale);
-      };
-      auto finalize = [&](int M) {
-        const int hh = M >> 1, tile = M & 1;
-        const float inv = 1.0f / acc[8];  // sum of the rounded probabilities, rescaled like the numerators
+        warp_arrive_a(BAR(B_OF + acc_i));
+        const float den = __uint_as_float(o[8]);  // sum of the rounded probabilities (ones row of V^T)
+        overflow |= !(den < 1e30f);                // inf / NaN: some P overflowed fp16 -> exact kernel redoes the unit
+        const float inv = 1.0f / den;
+        const float* bv = s_bias[g] + 64 + 8 * hh;
         const int64_t row = (int64_t)chunk * 256 + tile * 128 + tid;
-        *reinterpret_cast<uint4*>(o16 + row * 64 + (g * 4 + hh) * 8) =
-            make_uint4(pack_half2(acc[0] * inv, acc[1] * inv), pack_half2(acc[2] * inv, acc[3] * inv),
-                       pack_half2(acc[4] * inv, acc[5] * inv), pack_half2(acc[6] * inv, acc[7] * inv));
+        float v[8];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) acc[i] = 0.f;
-        m_run = -INFINITY;
+        for (int i = 0; i < 8; ++i) v[i] = fmaf(__uint_as_float(o[i]), inv, bv[i]);
+        *reinterpret_cast<uint4*>(o16 + row * 64 + (g * 4 + hh) * 8) =
+            make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
       };
+      // Software-pipelined quarter loop: S(j+1) is probed (non-blocking) and its first 32 columns are loaded in the
+      // middle of quarter j, the other 32 right after the last exponential of quarter j, so that a quarter starts
+      // with its scores already in registers.
+      uint32_t cb, cpar;
+      ring.next(cb, cpar);
+      wait_a(BAR(B_S + cb), cpar, kErrAttS);
+      tcgen05_fence_after();
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(lane_addr + 64 * cb, ra);
+      tmem_ld_32x32(lane_addr + 64 * cb + 32, rb);
+      PHASE(3);
 #pragma unroll 1
-      for (int M = 0; M < 8; ++M, ++mg) {
-        const uint32_t par = mg & 1;
-        const float mp2 = mq[2], mp3 = mq[3];  // maxima of the previous (head, tile)'s quarters 2 and 3
+      for (int M = 0; M < 8; ++M) {
+        float mneg = 0.f;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          wait_bar(&bar_S[q], par, status, &s_abort, kErrAttS);
-          tcgen05_fence_after();
-          PHASE(3);
-          uint32_t ra[32], rb[32];
-          tmem_ld_32x32(lane_addr + 64 * q, ra);
-          tmem_ld_32x32(lane_addr + 64 * q + 32, rb);
+          const bool has_next = !(M == 7 && q == 3);
+          uint32_t nb = 0, npar = 0;
+          if (has_next) ring.next(nb, npar);
+          const uint32_t col = lane_addr + 64 * cb, ncol = lane_addr + 64 * nb;
           tmem_wait_ld();
-          float m = chunk_max<32>(ra, -INFINITY);
-          m = (q == 3) ? chunk_max<S2S_L_DEC - 224>(rb, m) : chunk_max<32>(rb, m);
-          mq[q] = m;
-          const float mneg = -m * kScale;
+          if (q == 1 && M > 0) take_O_finish(M - 1);  // its tcgen05.ld was issued in the middle of the previous quarter
+          if (q == 0) mneg = -chunk_max<32>(ra, -INFINITY) * kScale;  // the row's reference: max of its first 32 scores
           PHASE(4);
-          chunk_exp_store<32>(ra, kScale, mneg, lane_addr + 64 * q);
-          if (q == 3) chunk_exp_store<S2S_L_DEC - 224>(rb, kScale, mneg, lane_addr + 64 * q + 16);
-          else chunk_exp_store<32>(rb, kScale, mneg, lane_addr + 64 * q + 16);
+          chunk_exp_store<32>(ra, kScale, mneg, col);
+          if (q == 0 && M > 0) {  // O of the previous (head, tile): its last P.V was issued most of a quarter ago
+            take_O_issue();
+            tmem_ld_32x16(lane_addr + kOaccCol + 16 * ((M - 1) & 1), o);
+          }
+          bool ready = false;
+          if (has_next) {
+            ready = __all_sync(0xffffffffu, mbar_test_wait_a(BAR(B_S + nb), npar));
+            if (ready) {
+              tcgen05_fence_after();
+              tmem_ld_32x32(ncol, ra);
+            }
+          }
+          if (q == 3) chunk_exp_store<S2S_L_DEC - 224>(rb, kScale, mneg, col + 16);
+          else chunk_exp_store<32>(rb, kScale, mneg, col + 16);
+          PHASE(5);
+          if (has_next) {
+            if (!ready) {
+              wait_a(BAR(B_S + nb), npar, kErrAttS);
+              tcgen05_fence_after();
+              tmem_ld_32x32(ncol, ra);
+            }
+            tmem_ld_32x32(ncol + 32, rb);
+          }
+          PHASE(3);
           tmem_wait_st();
           tcgen05_fence_before();
-          warp_arrive(&bar_P[q]);
-          PHASE(5);
-          // the O of two quarters ago has had a whole quarter of softmax time to finish
-          if (q >= 2) {
-            take_O(q - 2, par, mq[q - 2]);
-          } else if (M > 0) {
-            take_O(q + 2, par ^ 1, q == 0 ? mp2 : mp3);
-            if (q == 1) finalize(M - 1);
-          }
+          warp_arrive_a(BAR(B_P + cb));
+          if (q == 3) { ob = cb; opar = cpar; }
+          cb = nb; cpar = npar;
           PHASE(6);
         }
       }
-      take_O(2, (mg - 1) & 1, mq[2]);
-      take_O(3, (mg - 1) & 1, mq[3]);
-      finalize(7);
+      take_O_issue();
+      tmem_ld_32x16(lane_addr + kOaccCol + 16, o);
+      tmem_wait_ld();
+      take_O_finish(7);
+      if (__any_sync(0xffffffffu, overflow) && lane == 0) {
+        unit_flags[unit] = 1;
+        atomicAdd(n_flagged, 1);
+      }
       tcgen05_fence_before();
-      warp_arrive(&bar_unit);
+      warp_arrive_a(BAR(B_UNIT));
       PHASE(7);
     }
   }

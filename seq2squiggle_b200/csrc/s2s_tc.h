@@ -12,7 +12,7 @@ struct TcState {
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled entry point
   int32_t* d_status = nullptr;   // device word set by a kernel whose mbarrier wait timed out
   // optional CUDA-event bracketing of the attention launches (bench.py roofline leg)
-  bool attn_v1 = true;           // S2S_ATTN_V1=1: the unpipelined attention kernel (A/B measurements)
+  bool attn_v1 = false;          // S2S_ATTN_V1=1: the unpipelined attention kernel (A/B measurements)
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_events;   // start/stop pairs
   int64_t prof_chunks = 0;
@@ -24,6 +24,7 @@ struct TcBuffers {
   __half* o16 = nullptr;    // [rows,64]  attention output (A operand of fc)
   __half* xe16 = nullptr;   // encoder: [chunks*16 (padded to 128), 64] fp16 residual-stream copy
   __half* oe16 = nullptr;   // encoder attention output
+  int32_t* flags = nullptr; // [0] = number of flagged units, [1..2*chunks] = per-unit overflow flags of k_tc_attn2
 };
 
 void tc_carve(TcBuffers& b, char* base, int64_t& off, int64_t batch_chunks);

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) k_tmem_mufu(int what, int reps, long long
   if (what == 0) {          // ld only
     for (int k = 0; k < reps; ++k) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) { tmem_ld_32x32(lane_addr + c * 32, r); tmem_wait_ld(); acc += __uint_as_float(r[k & 31]); }
+      for (int c = 0; c < 8; ++c) { tmem_ld_32x32(lane_addr + c * 32, r); tmem_wait_ld(); acc += __uint_as_float(r[0]) + __uint_as_float(r[31]); }
     }
   } else if (what == 1) {   // st only (x16)
     uint32_t v[16];
@@ -156,6 +156,74 @@ __global__ void __launch_bounds__(256) k_tmem_mufu(int what, int reps, long long
   if (warp == 0) tmem_dealloc<512>(s_base);
 }
 
+// The attention kernel's per-quarter tensor work, issued by an elected lane of warp 4 with clean uniform code:
+// [4 dependent TS N=16 MMAs + commit] and [1 SS N=64 MMA + commit]; measures issue time and issue->complete latency of
+// each, optionally while warps 0-3 hammer TMEM / MUFU with the exp pass (busy = 1) to expose interference.
+__global__ void __launch_bounds__(160) k_quarter_pattern(int busy, int reps, long long* out, float* sink) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint32_t s_base;
+  __shared__ __align__(8) uint64_t bar_pv, bar_s;
+  __shared__ volatile int s_stop;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 64 * 1024 / 16; i += 160) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 0) tmem_alloc<512>(&s_base);
+  if (tid == 0) { mbar_init(&bar_pv, 1); mbar_init(&bar_s, 1); fence_mbar_init(); s_stop = 0; }
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = s_base;
+  if (warp == 4) {
+    const uint64_t dA = umma_desc_k_sw128(smem_u32(smem)), dB = umma_desc_k_sw128(smem_u32(smem + 32768));
+    const uint32_t idesc_o = umma_idesc(128, 16, kFmtF16), idesc_s = umma_idesc(128, 64, kFmtF16);
+    long long t_issue_pv = 0, t_lat_pv = 0, t_issue_s = 0, t_lat_s = 0;
+    for (int r = 0; r < reps; ++r) {
+      long long t0 = clock64();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_f16_ts(tmem + 448, tmem + 256 + 8 * ks, dB + (uint64_t)(ks * 2), idesc_o, ks > 0);
+        umma_commit(&bar_pv);
+      }
+      long long t1 = clock64();
+      while (!mbar_try_wait(&bar_pv, r & 1)) {}
+      long long t2 = clock64();
+      if (elect_one()) {
+        umma_f16_ss(tmem + 320, dA, dB, idesc_s, 0);
+        umma_commit(&bar_s);
+      }
+      long long t3 = clock64();
+      while (!mbar_try_wait(&bar_s, r & 1)) {}
+      long long t4 = clock64();
+      t_issue_pv += t1 - t0; t_lat_pv += t2 - t0; t_issue_s += t3 - t2; t_lat_s += t4 - t2;
+    }
+    if ((tid & 31) == 0) { out[0] = t_issue_pv; out[1] = t_lat_pv; out[2] = t_issue_s; out[3] = t_lat_s; }
+    s_stop = 1;
+  } else if (busy) {
+    const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
+    uint32_t r[32];
+    float acc = 0.f;
+    while (!s_stop) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        tmem_ld_32x32(lane_addr + c * 32, r);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          pk[i] = pack_half2(ex2f(fmaf(__uint_as_float(r[2 * i]), 0.5f, -1.f)), ex2f(fmaf(__uint_as_float(r[2 * i + 1]), 0.5f, -1.f)));
+        tmem_st_32x16(lane_addr + c * 16, pk);
+      }
+      tmem_wait_st();
+      acc += __uint_as_float(r[0]);
+    }
+    sink[tid] = acc;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 int main() {
   long long* out;
   float* sink;
@@ -180,6 +248,16 @@ int main() {
       printf("%s batch %2d: issue %6.1f clk/MMA  pipelined %6.1f clk/MMA  round trip (issue+commit+wait) %6.0f clk/batch  [%s]\n",
              s.name, batch, (double)issue / (reps * batch), (double)total / (reps * batch), (double)h[0] / reps, cudaGetErrorString(e));
     }
+  }
+  cudaFuncSetAttribute(k_quarter_pattern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  for (int busy = 0; busy < 2; ++busy) {
+    const int reps = 200;
+    k_quarter_pattern<<<1, 160, 100 * 1024>>>(busy, reps, out, sink);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(h, out, sizeof h, cudaMemcpyDeviceToHost);
+    printf("quarter pattern (softmax warps %s): P.V 4xTS N=16 + commit: issue %5.0f clk, issue->complete %5.0f clk | S 1xSS N=64 + commit: "
+           "issue %5.0f clk, issue->complete %5.0f clk [%s]\n", busy ? "busy" : "idle", (double)h[0] / reps, (double)h[1] / reps,
+           (double)h[2] / reps, (double)h[3] / reps, cudaGetErrorString(e));
   }
   const char* names[] = {"tcgen05.ld x32 (+wait) ", "tcgen05.st x16         ", "ex2.approx             ", "ld+ffma+ex2+pack+st    "};
   for (int what = 0; what < 4; ++what) {

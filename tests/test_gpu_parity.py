@@ -281,3 +281,45 @@ def test_shard_invariance(golden_dir):
     b, _ = eng.forward_reads(reads[3:], opts, chunk_id_base=n0)
     for x, y in zip(whole, a + b):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("scale", [3.0, 4.5, 9.0])
+def test_attention_overflow_falls_back_to_exact_kernel(golden_dir, scale):
+    """The pipelined attention kernel uses one reference maximum per row (max of its first 32 scores) and flags a
+    (chunk, head group) whose fp16 probabilities overflowed; the exact two-pass kernel recomputes the flagged units.
+    Scaling W_q/W_k of the decoder makes scores differ by far more than the fp16 range allows, so the fallback must
+    trigger, and the result must equal the exact kernel run on its own (S2S_ATTN_V1=1)."""
+    import ctypes as C
+    from seq2squiggle_b200 import _lib
+    from seq2squiggle_b200.engine import Engine
+    ck = torch.load(os.path.join(golden_dir, "ckpt_k9_seed1.ckpt"), map_location="cpu", weights_only=False)
+    sd, cfg = dict(ck["state_dict"]), ck["hyper_parameters"]["config"]
+    for layer in (0, 1):
+        for name in ("w_qs", "w_ks"):
+            for part in ("weight", "bias"):
+                key = f"decoders.layer_stack_FFT.{layer}.slf_attn.{name}.{part}"
+                sd[key] = sd[key] * scale
+    fx = np.load(os.path.join(golden_dir, "predict_k9_ideal.npz"))
+    codes = torch.from_numpy(fx["codes"]).cuda()
+    opts = _opts("dna-r10-prom", "fp16", dwell_mean=12.5)
+    lib = _lib.load()
+    counters = (C.c_int64 * 16)()
+    lib.s2s_debug_counters(counters, 16, 1)
+    fast = Engine(sd, cfg, device=0)
+    pa_fast, _ = fast.forward_chunks(codes, opts)
+    lib.s2s_debug_counters(counters, 16, 1)
+    flagged = counters[12]
+    os.environ["S2S_ATTN_V1"] = "1"
+    try:
+        exact = Engine(sd, cfg, device=0)
+    finally:
+        del os.environ["S2S_ATTN_V1"]
+    pa_exact, _ = exact.forward_chunks(codes, opts)
+    a, b = pa_fast.cpu().numpy(), pa_exact.cpu().numpy()
+    if scale >= 9.0:
+        assert flagged > 0, "the scaled checkpoint was meant to overflow the single-reference softmax"
+    assert np.isfinite(a).all() and np.isfinite(b).all()
+    ref = orc.predict_step(sd, cfg, torch.from_numpy(orc.split_sequence_fast(str(fx["read_seqs"][0]), cfg)[:1]),
+                           dwell_mean=12.5, min_duration=3).numpy()
+    assert np.abs(a - b).max() <= 0.02 * max(16.5, np.abs(b).max()), np.abs(a - b).max()
+    print(f"scale {scale}: flagged units: {flagged} of {4 * codes.shape[0]}; max |fast - exact| = {np.abs(a - b).max():.4g}; oracle row0 max {ref.max():.3g}")
