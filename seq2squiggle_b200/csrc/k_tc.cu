@@ -135,6 +135,39 @@ __device__ __forceinline__ void chunk_exp_store(const uint32_t (&r)[32], float s
   tmem_st_32x16(taddr, pk);
 }
 
+// 2^x on the FMA/ALU pipes instead of MUFU (the attention kernel is bound by the 16 ex2/clk/SM of the XU pipe):
+// round-to-nearest split x = n + f with the 1.5*2^23 magic constant, degree-3 minimax polynomial for 2^f on
+// [-0.5, 0.5] (max relative error 7.5e-5, well under the 4.9e-4 half-ulp of the fp16 P it is rounded to), exponent
+// add by one integer LEA.  Clamped to [-30, 64]: below is 0 in fp16 anyway, above still overflows fp16 to inf, which is
+// what flags the unit for the exact kernel.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fminf(fmaxf(x, -30.0f), 64.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(0.05517167f, f, 0.24261113f);
+  p = fmaf(p, f, 0.69326097f);
+  p = fmaf(p, f, 0.99992806f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// chunk_exp_store with kPoly of every 32 exponentials taken off the MUFU pipe (evenly interleaved)
+template <int kValid, int kPoly>
+__device__ __forceinline__ void chunk_exp_store_mixed(const uint32_t (&r)[32], float scale, float mneg, uint32_t taddr) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float p[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int e = 2 * i + h;
+      const float x = fmaf(__uint_as_float(r[e]), scale, mneg);
+      p[h] = e < kValid ? (((e * kPoly) % 32 < kPoly) ? ex2_poly(x) : ex2_approx(x)) : 0.f;
+    }
+    pk[i] = pack_half2(p[0], p[1]);
+  }
+  tmem_st_32x16(taddr, pk);
+}
+
 __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUtensorMap tmX,
                                                     const __grid_constant__ CUtensorMap tmWg,
                                                     const float* __restrict__ bias_g, __half* __restrict__ o16,

@@ -22,6 +22,10 @@
 #pragma once
 
 constexpr int kAttn2Threads = 160;
+#ifndef S2S_POLY_EXP
+#define S2S_POLY_EXP 0
+#endif
+constexpr int kPolyExp = S2S_POLY_EXP;  // exponentials per 32 computed on the FMA pipe instead of MUFU
 
 __device__ __forceinline__ void warp_arrive(uint64_t* bar) {
   __syncwarp();
@@ -115,6 +119,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
     const uint64_t dXQ = umma_desc_k_sw128(aXQ), dK = umma_desc_k_sw128(smem_u32(sK)), dV = umma_desc_k_sw128(smem_u32(sV));
     uint32_t it = 0, ph_w = 0;
     int cur_g = -1;
+    bool x_prefetched = false;
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
       const int chunk = unit >> 1, g = unit & 1;
       const uint32_t upar = it & 1;
@@ -123,10 +128,13 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
           mbar_arrive_expect_tx(&bars[B_W], 96 * 128);
           tma_load_2d(sW, &tmWg, &bars[B_W], 0, g * 96);
         }
-        mbar_arrive_expect_tx(&bars[B_LOAD], 2 * kSlab);
-        tma_load_2d(sXQ, &tmX, &bars[B_LOAD], 0, chunk * 256);
-        tma_load_2d(sXQ + kSlab, &tmX, &bars[B_LOAD], 0, chunk * 256 + 128);
+        if (!x_prefetched) {
+          mbar_arrive_expect_tx(&bars[B_LOAD], 2 * kSlab);
+          tma_load_2d(sXQ, &tmX, &bars[B_LOAD], 0, chunk * 256);
+          tma_load_2d(sXQ + kSlab, &tmX, &bars[B_LOAD], 0, chunk * 256 + 128);
+        }
       }
+      x_prefetched = false;
       if (g != cur_g) {
         wait_a(BAR(B_W), ph_w, kErrAttLoad);
         ph_w ^= 1;
@@ -183,6 +191,21 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
           PHASE(12);
           if (elect_one()) issue_S(j + 3, b);
           PHASE(13);
+          if (j + 3 == 31) {
+            // The unit's last S has been issued.  Once it completes nothing reads the Q tiles any more, so the next
+            // unit's X tiles can stream into sXQ during the last three quarters (hides the ~1.5k clk TMA latency).
+            const int next_unit = unit + (int)gridDim.x;
+            if (next_unit < n_units && (next_unit & 1) == g) {
+              wait_a(BAR(B_S + b), par ^ 1u, kErrAttLoad);
+              if (elect_one()) {
+                const int nchunk = next_unit >> 1;
+                mbar_arrive_expect_tx(&bars[B_LOAD], 2 * kSlab);
+                tma_load_2d(sXQ, &tmX, &bars[B_LOAD], 0, nchunk * 256);
+                tma_load_2d(sXQ + kSlab, &tmX, &bars[B_LOAD], 0, nchunk * 256 + 128);
+              }
+              x_prefetched = true;
+            }
+          }
         }
       }
       // every softmax warp has read its last O: shared-memory operands and TMEM may be overwritten
@@ -286,7 +309,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
           if (q == 1 && M > 0) take_O_finish(M - 1);  // its tcgen05.ld was issued in the middle of the previous quarter
           if (q == 0) mneg = -chunk_max<32>(ra, -INFINITY) * kScale;  // the row's reference: max of its first 32 scores
           PHASE(4);
-          chunk_exp_store<32>(ra, kScale, mneg, col);
+          chunk_exp_store_mixed<32, kPolyExp>(ra, kScale, mneg, col);
           if (q == 0 && M > 0) {  // O of the previous (head, tile): its last P.V was issued most of a quarter ago
             take_O_issue();
             tmem_ld_32x16(lane_addr + kOaccCol + 16 * ((M - 1) & 1), o);
@@ -299,8 +322,8 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
               tmem_ld_32x32(ncol, ra);
             }
           }
-          if (q == 3) chunk_exp_store<S2S_L_DEC - 224>(rb, kScale, mneg, col + 16);
-          else chunk_exp_store<32>(rb, kScale, mneg, col + 16);
+          if (q == 3) chunk_exp_store_mixed<S2S_L_DEC - 224, kPolyExp>(rb, kScale, mneg, col + 16);
+          else chunk_exp_store_mixed<32, kPolyExp>(rb, kScale, mneg, col + 16);
           PHASE(5);
           if (has_next) {
             if (!ready) {

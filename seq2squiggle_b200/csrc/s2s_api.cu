@@ -31,7 +31,8 @@ struct s2s_engine {
   float* d_f32 = nullptr;   // derived fp32 weights
   __half* d_f16 = nullptr;  // fp16 operand copies (tcgen05 path)
   DevWeights dw{};
-  int64_t batch_chunks = 4096;
+  int64_t batch_chunks = 16384;  // chunks per sub-batch of the tensor-core path (S2S_BATCH_CHUNKS)
+  int64_t batch_chunks_f32 = 1024;  // fp32 parity path: its fp32 scratch is 2.6 MB per chunk
   TcState tc{};
 };
 
@@ -162,7 +163,8 @@ struct Workspace {
 int64_t carve(Workspace& w, void* base, const s2s_engine* h, int64_t n_chunks, int64_t n_reads, bool need_pa) {
   Carver cv(base);
   const int64_t bc = n_chunks < h->batch_chunks ? n_chunks : h->batch_chunks;
-  const int64_t me = bc * S2S_L_ENC, md = bc * S2S_L_DEC_PAD;
+  const int64_t bc32 = n_chunks < h->batch_chunks_f32 ? n_chunks : h->batch_chunks_f32;  // fp32-only buffers
+  const int64_t me = bc * S2S_L_ENC, md = bc * S2S_L_DEC_PAD, md32 = bc32 * S2S_L_DEC_PAD;
   w.chunk_read = cv.take<int32_t>(n_chunks);
   w.chunk_nk = cv.take<int32_t>(n_chunks);
   w.chunk_base = cv.take<int64_t>(n_chunks);
@@ -179,11 +181,11 @@ int64_t carve(Workspace& w, void* base, const s2s_engine* h, int64_t n_chunks, i
   w.sigma = cv.take<float>(me);
   w.dur = cv.take<int32_t>(me);
   w.total = cv.take<int32_t>(bc);
-  w.xd = cv.take<float>(md * 64);
-  w.qkv_d = cv.take<float>(md * 192);
-  w.att_d = cv.take<float>(md * 64);
-  w.yd = cv.take<float>(md * 64);
-  w.hd = cv.take<float>(md * 256);
+  w.xd = cv.take<float>(md32 * 64);
+  w.qkv_d = cv.take<float>(md32 * 192);
+  w.att_d = cv.take<float>(md32 * 64);
+  w.yd = cv.take<float>(md32 * 64);
+  w.hd = cv.take<float>(md32 * 256);
   w.sigma_ext = cv.take<float>(bc * S2S_L_DEC);
   w.p_rows = cv.take<float>(md);
   tc_carve(w.tcb, cv.base, cv.off, bc);
@@ -214,8 +216,9 @@ int run_pipeline(s2s_engine* h, const uint8_t* bases, const int8_t* codes, const
   const DevWeights& dw = h->dw;
   const int k = h->cfg.seq_kmer;
   const bool tc_path = opts.precision == S2S_PREC_FP16_TC;
-  for (int64_t c0 = 0; c0 < n_chunks; c0 += h->batch_chunks) {
-    const int64_t bc = (n_chunks - c0) < h->batch_chunks ? (n_chunks - c0) : h->batch_chunks;
+  const int64_t step = tc_path ? h->batch_chunks : (h->batch_chunks_f32 < h->batch_chunks ? h->batch_chunks_f32 : h->batch_chunks);
+  for (int64_t c0 = 0; c0 < n_chunks; c0 += step) {
+    const int64_t bc = (n_chunks - c0) < step ? (n_chunks - c0) : step;
     const int64_t me = bc * S2S_L_ENC;
     s2s_run_opts o = opts;
     o.chunk_id_base = opts.chunk_id_base + (uint64_t)c0;

@@ -17,6 +17,77 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split with the 1.5*2^23 magic constant, degree-3 minimax
+// polynomial on [-0.5, 0.5] (max relative error 7.5e-5, far below the fp16 rounding of P), exponent add by LEA.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -30.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(0.05517167f, f, 0.24261113f);
+  p = fmaf(p, f, 0.69326097f);
+  p = fmaf(p, f, 0.99992806f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// the exp pass with K of every 32 exponentials computed by ex2_poly
+template <int K>
+__device__ __forceinline__ void exp_step_mixed(const uint32_t (&r)[32], uint32_t taddr) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float x0 = fmaf(__uint_as_float(r[2 * i]), 0.5f, -1.f), x1 = fmaf(__uint_as_float(r[2 * i + 1]), 0.5f, -1.f);
+    const bool poly0 = ((2 * i) * K) % 32 < K, poly1 = ((2 * i + 1) * K) % 32 < K;
+    pk[i] = pack_half2(poly0 ? ex2_poly(x0) : ex2f(x0), poly1 ? ex2_poly(x1) : ex2f(x1));
+  }
+  tmem_st_32x16(taddr, pk);
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) k_exp_mixed(int reps, long long* out, float* sink) {
+  __shared__ uint32_t s_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc<512>(&s_base);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t lane_addr = tmem_addr(s_base, (warp & 3) * 32, (warp >> 2) * 256);
+  uint32_t ra[32], rb[32];
+  __syncthreads();
+  long long t0 = clock64();
+  for (int k = 0; k < reps; ++k) {  // double-buffered loads like the kernel
+    tmem_ld_32x32(lane_addr, ra);
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+      tmem_ld_32x32(lane_addr + (c + 1) * 32, rb);
+      tmem_wait_ld();   // (waits for both; the second has the whole step to land in the real kernel)
+      exp_step_mixed<K>(ra, lane_addr + c * 16);
+      if (c + 2 < 8) tmem_ld_32x32(lane_addr + (c + 2) * 32, ra);
+      exp_step_mixed<K>(rb, lane_addr + (c + 1) * 16);
+    }
+    tmem_wait_st();
+  }
+  long long t1 = clock64();
+  if ((tid & 31) == 0) out[warp] = t1 - t0;
+  sink[tid] = __uint_as_float(ra[0]);
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(s_base);
+}
+
+template <int K>
+void run_exp_mixed(long long* out, float* sink) {
+  long long h[16];
+  for (int threads : {128, 256}) {
+    const int reps = 200;
+    k_exp_mixed<K><<<1, threads>>>(reps, out, sink);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(h, out, sizeof h, cudaMemcpyDeviceToHost);
+    double per = (double)h[0] / (reps * 8);
+    printf("exp pass, %2d/32 polynomial, %d warps/scheduler: %6.1f clk per 32-column step per warp  -> %5.2f clk per exp row per scheduler [%s]\n",
+           K, threads / 128, per, per / 32 / (threads / 128), cudaGetErrorString(e));
+  }
+}
+
 // mode 0: SS (A,B smem), mode 1: TS (A tmem).  n = MMA N.  batch MMAs then one commit, repeated `reps` times
 // back to back; out[0] = clocks spent issuing, out[1] = clocks until the last commit's barrier flips.
 __global__ void __launch_bounds__(128) k_mma_timing(int mode, int n, int batch, int reps, long long* out) {
@@ -259,6 +330,8 @@ int main() {
            "issue %5.0f clk, issue->complete %5.0f clk [%s]\n", busy ? "busy" : "idle", (double)h[0] / reps, (double)h[1] / reps,
            (double)h[2] / reps, (double)h[3] / reps, cudaGetErrorString(e));
   }
+  run_exp_mixed<0>(out, sink); run_exp_mixed<4>(out, sink); run_exp_mixed<8>(out, sink); run_exp_mixed<10>(out, sink);
+  run_exp_mixed<12>(out, sink); run_exp_mixed<16>(out, sink);
   const char* names[] = {"tcgen05.ld x32 (+wait) ", "tcgen05.st x16         ", "ex2.approx             ", "ld+ffma+ex2+pack+st    "};
   for (int what = 0; what < 4; ++what) {
     for (int threads : {128, 256}) {
