@@ -8,7 +8,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(HERE, "libs2s_b200.so")
+# S2S_LIB_PATH: developer override to build / load an experimental variant next to the shipped library
+LIB_PATH = os.environ.get("S2S_LIB_PATH") or os.path.join(HERE, "libs2s_b200.so")
 SOURCES = ["s2s_api.cu", "k_frontend.cu", "k_simt.cu", "k_samplers.cu", "k_length_regulate.cu", "k_epilogue.cu",
            "k_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -25,7 +25,11 @@ constexpr int kAttn2Threads = 160;
 #ifndef S2S_POLY_EXP
 #define S2S_POLY_EXP 0
 #endif
-constexpr int kPolyExp = S2S_POLY_EXP;  // exponentials per 32 computed on the FMA pipe instead of MUFU
+constexpr int kPolyExp = S2S_POLY_EXP;  // exponentials per 32 computed on the FMA pipe (fp32 polynomial) instead of MUFU
+#ifndef S2S_POLY_EXP_H2
+#define S2S_POLY_EXP_H2 4
+#endif
+constexpr int kPolyExpH2 = S2S_POLY_EXP_H2;  // pairs per 16 computed by the packed-fp16 polynomial instead of MUFU
 
 __device__ __forceinline__ void warp_arrive(uint64_t* bar) {
   __syncwarp();
@@ -309,7 +313,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
           if (q == 1 && M > 0) take_O_finish(M - 1);  // its tcgen05.ld was issued in the middle of the previous quarter
           if (q == 0) mneg = -chunk_max<32>(ra, -INFINITY) * kScale;  // the row's reference: max of its first 32 scores
           PHASE(4);
-          chunk_exp_store_mixed<32, kPolyExp>(ra, kScale, mneg, col);
+          chunk_exp_store_mixed<32, kPolyExp, kPolyExpH2>(ra, kScale, mneg, col);
           if (q == 0 && M > 0) {  // O of the previous (head, tile): its last P.V was issued most of a quarter ago
             take_O_issue();
             tmem_ld_32x16(lane_addr + kOaccCol + 16 * ((M - 1) & 1), o);
@@ -322,8 +326,8 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
               tmem_ld_32x32(ncol, ra);
             }
           }
-          if (q == 3) chunk_exp_store_mixed<S2S_L_DEC - 224, kPolyExp>(rb, kScale, mneg, col + 16);
-          else chunk_exp_store_mixed<32, kPolyExp>(rb, kScale, mneg, col + 16);
+          if (q == 3) chunk_exp_store_mixed<S2S_L_DEC - 224, kPolyExp, kPolyExpH2>(rb, kScale, mneg, col + 16);
+          else chunk_exp_store_mixed<32, kPolyExp, kPolyExpH2>(rb, kScale, mneg, col + 16);
           PHASE(5);
           if (has_next) {
             if (!ready) {

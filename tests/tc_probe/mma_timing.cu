@@ -4,6 +4,7 @@
 //     PV: TS N=16 K=16, QKV: SS N=96) as a function of the batch size between commits;
 //   * tcgen05.ld / st throughput per warp; MUFU.EX2 throughput for 1 and 2 warps per scheduler.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o mma_timing mma_timing.cu ; run on the GPU box.
+#include <cuda_fp16.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -42,7 +43,40 @@ __device__ __forceinline__ void exp_step_mixed(const uint32_t (&r)[32], uint32_t
   tmem_st_32x16(taddr, pk);
 }
 
+// 2^x for a PAIR of scores in packed fp16 arithmetic (HFMA2/HADD2 on the FMA pipe, no MUFU): x rounded to fp16,
+// n = rint(x) via the 1536+15 magic constant (its low 5 mantissa bits are n+15 = the fp16 exponent field of 2^n),
+// degree-3 polynomial on f = x - n, result = p * 2^n by one HMUL2.  Clamped to [-15, 16] (2^16 overflows to inf).
+__device__ __forceinline__ uint32_t ex2_poly_h2(float x0, float x1) {
+  const __half2 kLo = __float2half2_rn(-15.0f), kHi = __float2half2_rn(16.0f), kMagic = __float2half2_rn(1551.0f);
+  __half2 x = __hmin2(__hmax2(__floats2half2_rn(x0, x1), kLo), kHi);
+  const __half2 t = __hadd2(x, kMagic);
+  const __half2 f = __hsub2(x, __hsub2(t, kMagic));
+  __half2 p = __hfma2(__float2half2_rn(0.05517167f), f, __float2half2_rn(0.24261113f));
+  p = __hfma2(p, f, __float2half2_rn(0.69326097f));
+  p = __hfma2(p, f, __float2half2_rn(0.99992806f));
+  const uint32_t sc = (*reinterpret_cast<const uint32_t*>(&t) << 10) & 0x7C007C00u;
+  const __half2 r = __hmul2(p, *reinterpret_cast<const __half2*>(&sc));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+// exp pass with K of every 16 PAIRS computed by ex2_poly_h2 (H2 = 1) instead of MUFU
 template <int K>
+__device__ __forceinline__ void exp_step_mixed_h2(const uint32_t (&r)[32], uint32_t taddr) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float x0 = fmaf(__uint_as_float(r[2 * i]), 0.5f, -1.f), x1 = fmaf(__uint_as_float(r[2 * i + 1]), 0.5f, -1.f);
+    pk[i] = ((i * K) % 16 < K) ? ex2_poly_h2(x0, x1) : pack_half2(ex2f(x0), ex2f(x1));
+  }
+  tmem_st_32x16(taddr, pk);
+}
+
+template <int K, int H2>
+__device__ __forceinline__ void exp_step_sel(const uint32_t (&r)[32], uint32_t taddr) {
+  if constexpr (H2) exp_step_mixed_h2<K>(r, taddr); else exp_step_mixed<K>(r, taddr);
+}
+
+template <int K, int H2 = 0>
 __global__ void __launch_bounds__(256) k_exp_mixed(int reps, long long* out, float* sink) {
   __shared__ uint32_t s_base;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -60,9 +94,9 @@ __global__ void __launch_bounds__(256) k_exp_mixed(int reps, long long* out, flo
     for (int c = 0; c < 8; c += 2) {
       tmem_ld_32x32(lane_addr + (c + 1) * 32, rb);
       tmem_wait_ld();   // (waits for both; the second has the whole step to land in the real kernel)
-      exp_step_mixed<K>(ra, lane_addr + c * 16);
+      exp_step_sel<K, H2>(ra, lane_addr + c * 16);
       if (c + 2 < 8) tmem_ld_32x32(lane_addr + (c + 2) * 32, ra);
-      exp_step_mixed<K>(rb, lane_addr + (c + 1) * 16);
+      exp_step_sel<K, H2>(rb, lane_addr + (c + 1) * 16);
     }
     tmem_wait_st();
   }
@@ -74,17 +108,17 @@ __global__ void __launch_bounds__(256) k_exp_mixed(int reps, long long* out, flo
   if (warp == 0) tmem_dealloc<512>(s_base);
 }
 
-template <int K>
+template <int K, int H2 = 0>
 void run_exp_mixed(long long* out, float* sink) {
   long long h[16];
   for (int threads : {128, 256}) {
     const int reps = 200;
-    k_exp_mixed<K><<<1, threads>>>(reps, out, sink);
+    k_exp_mixed<K, H2><<<1, threads>>>(reps, out, sink);
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(h, out, sizeof h, cudaMemcpyDeviceToHost);
     double per = (double)h[0] / (reps * 8);
-    printf("exp pass, %2d/32 polynomial, %d warps/scheduler: %6.1f clk per 32-column step per warp  -> %5.2f clk per exp row per scheduler [%s]\n",
-           K, threads / 128, per, per / 32 / (threads / 128), cudaGetErrorString(e));
+    printf("exp pass, %2d/%d polynomial%s, %d warps/scheduler: %6.1f clk per 32-column step per warp  -> %5.2f clk per exp row per scheduler [%s]\n",
+           K, H2 ? 16 : 32, H2 ? " (half2 pairs)" : "", threads / 128, per, per / 32 / (threads / 128), cudaGetErrorString(e));
   }
 }
 
@@ -204,6 +238,16 @@ __global__ void __launch_bounds__(256) k_tmem_mufu(int what, int reps, long long
         for (int i = 0; i < 32; ++i) x[i] = ex2f(x[i]) - 1.0f;
     }
     for (int i = 0; i < 32; ++i) acc += x[i];
+  } else if (what == 4) {   // MUFU.EX2.F16 (ex2.approx.f16x2 = two MUFU.EX2.F16): 512 exponentials per thread per rep
+    uint32_t x[32];
+    for (int i = 0; i < 32; ++i) x[i] = 0xB800B800u + tid + i;
+    for (int k = 0; k < reps; ++k) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(x[i]) : "r"(x[i])); x[i] ^= 0x80008000u; }
+    }
+    for (int i = 0; i < 32; ++i) acc += __uint_as_float(x[i]);
   } else {                  // ld + ex2 + pack + st, the exp pass of the kernel
     for (int k = 0; k < reps; ++k) {
 #pragma unroll
@@ -332,8 +376,11 @@ int main() {
   }
   run_exp_mixed<0>(out, sink); run_exp_mixed<4>(out, sink); run_exp_mixed<8>(out, sink); run_exp_mixed<10>(out, sink);
   run_exp_mixed<12>(out, sink); run_exp_mixed<16>(out, sink);
-  const char* names[] = {"tcgen05.ld x32 (+wait) ", "tcgen05.st x16         ", "ex2.approx             ", "ld+ffma+ex2+pack+st    "};
-  for (int what = 0; what < 4; ++what) {
+  run_exp_mixed<4, 1>(out, sink); run_exp_mixed<6, 1>(out, sink); run_exp_mixed<7, 1>(out, sink); run_exp_mixed<8, 1>(out, sink);
+  run_exp_mixed<10, 1>(out, sink); run_exp_mixed<16, 1>(out, sink);
+  const char* names[] = {"tcgen05.ld x32 (+wait) ", "tcgen05.st x16         ", "ex2.approx             ", "ld+ffma+ex2+pack+st    ",
+                         "ex2.approx.f16x2 (2/op)"};
+  for (int what = 0; what < 5; ++what) {
     for (int threads : {128, 256}) {
       const int reps = 200;
       k_tmem_mufu<<<1, threads>>>(what, reps, out, sink);
