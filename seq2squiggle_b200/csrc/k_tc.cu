@@ -412,6 +412,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUte
 }
 
 #include "k_tc_attn2.cuh"
+#include "k_tc_attn4.cuh"
 
 // =================================================================================================
 // FFN: X' = LN2(relu(Y W1^T + b1) W2^T + b2 + Y) with Y = LN1(O Wfc^T + b + X), one kernel, 128 rows per
@@ -753,6 +754,7 @@ int tc_init(TcState& s, const DevWeights& w, int device) {
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_qkv_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemQkv));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn2, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn4, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt));
   if (const char* env = getenv("S2S_ATTN_V1")) s.attn_v1 = atoi(env) != 0;
   if (const char* env = getenv("S2S_ATTN_V2")) s.attn_v1 = atoi(env) == 0;
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
@@ -811,8 +813,16 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* p_out
       static const bool one_cta = getenv("S2S_ATTN_1CTA") && atoi(getenv("S2S_ATTN_1CTA"));
       const int grid2a = one_cta ? (n_units < s.sm_count ? n_units : s.sm_count) : grid_att;
       const int smem2a = one_cta ? 150 * 1024 : kSmemAtt;
-      k_tc_attn2<<<grid2a, kAttn2Threads, smem2a, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags,
-                                                           s.d_status);
+      // S2S_ATTN_VER=4 selects k_tc_attn4 (16 softmax warps per SM): parity-green but measured SLOWER than k_tc_attn2
+      // (2.96 vs 2.40 ms per 16384 chunks): with 4-5 busy warps per scheduler the MMA issue warps get too few issue slots
+      // and the softmax warps wait for S (profiles/r01_attn4_experiment.txt).
+      static const int attn_ver = getenv("S2S_ATTN_VER") ? atoi(getenv("S2S_ATTN_VER")) : 2;
+      if (attn_ver != 4)
+        k_tc_attn2<<<grid2a, kAttn2Threads, smem2a, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags,
+                                                             s.d_status);
+      else
+        k_tc_attn4<<<grid_att, kAttn4Threads, kSmemAtt, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags,
+                                                              s.d_status);
       S2S_LAUNCH_CHECK();
       k_tc_attn<<<grid_att, 128, kSmemAtt, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags, s.d_status);
     }

@@ -77,14 +77,15 @@ __device__ __forceinline__ void exp_step_sel(const uint32_t (&r)[32], uint32_t t
 }
 
 template <int K, int H2 = 0>
-__global__ void __launch_bounds__(256) k_exp_mixed(int reps, long long* out, float* sink) {
+__global__ void __launch_bounds__(512) k_exp_mixed(int reps, long long* out, float* sink) {
   __shared__ uint32_t s_base;
   const int tid = threadIdx.x, warp = tid >> 5;
   if (warp == 0) tmem_alloc<512>(&s_base);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t lane_addr = tmem_addr(s_base, (warp & 3) * 32, (warp >> 2) * 256);
+  // every warp owns 128 columns (4 chunks of 32) of its lane quarter: up to 4 warps per scheduler
+  const uint32_t lane_addr = tmem_addr(s_base, (warp & 3) * 32, (warp >> 2) * 128);
   uint32_t ra[32], rb[32];
   __syncthreads();
   long long t0 = clock64();
@@ -92,11 +93,11 @@ __global__ void __launch_bounds__(256) k_exp_mixed(int reps, long long* out, flo
     tmem_ld_32x32(lane_addr, ra);
 #pragma unroll
     for (int c = 0; c < 8; c += 2) {
-      tmem_ld_32x32(lane_addr + (c + 1) * 32, rb);
+      tmem_ld_32x32(lane_addr + ((c + 1) & 3) * 32, rb);
       tmem_wait_ld();   // (waits for both; the second has the whole step to land in the real kernel)
-      exp_step_sel<K, H2>(ra, lane_addr + c * 16);
-      if (c + 2 < 8) tmem_ld_32x32(lane_addr + (c + 2) * 32, ra);
-      exp_step_sel<K, H2>(rb, lane_addr + (c + 1) * 16);
+      exp_step_sel<K, H2>(ra, lane_addr + (c & 3) * 16);
+      if (c + 2 < 8) tmem_ld_32x32(lane_addr + ((c + 2) & 3) * 32, ra);
+      exp_step_sel<K, H2>(rb, lane_addr + ((c + 1) & 3) * 16);
     }
     tmem_wait_st();
   }
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(256) k_exp_mixed(int reps, long long* out, flo
 template <int K, int H2 = 0>
 void run_exp_mixed(long long* out, float* sink) {
   long long h[16];
-  for (int threads : {128, 256}) {
+  for (int threads : {128, 256, 384, 512}) {
     const int reps = 200;
     k_exp_mixed<K, H2><<<1, threads>>>(reps, out, sink);
     cudaError_t e = cudaDeviceSynchronize();
