@@ -483,6 +483,12 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
       tma_load_2d(sA, &tmA, &bar_a[0], 0, tile * 128);
     }
   }
+  uint4 xr[8];  // decoder: fp16 residual row of the current tile, loaded one tile ahead
+  if (!kRes32 && tile < n_tiles) {
+    const uint4* rp = reinterpret_cast<const uint4*>(x16 + ((int64_t)tile * 128 + tid) * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xr[i] = rp[i];
+  }
   wait_bar(&bar_w, 0, status, &s_abort, kErrFfnLoad);
   const uint32_t idesc64 = umma_idesc(128, 64, kFmtF16), idesc256 = umma_idesc(128, 256, kFmtF16);
   for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -514,10 +520,11 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
         y[4 * i + 2] = x.z + s_v[0][4 * i + 2]; y[4 * i + 3] = x.w + s_v[0][4 * i + 3];
       }
     } else {
-      const uint4* rp = reinterpret_cast<const uint4*>(x16 + row * 64);
+      // the row was fetched one tile ahead (xr): a thread's 128-byte row is eight scattered 16-byte loads whose DRAM
+      // latency (~1.5k clk) would otherwise sit on the critical path in front of LayerNorm 1
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const uint4 x = rp[i];
+        const uint4 x = xr[i];
         const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -525,6 +532,11 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
           y[8 * i + 2 * j] = f.x + s_v[0][8 * i + 2 * j];
           y[8 * i + 2 * j + 1] = f.y + s_v[0][8 * i + 2 * j + 1];
         }
+      }
+      if (next < n_tiles) {  // tile `next` is only ever touched by this CTA: its rows are still the block input
+        const uint4* rp = reinterpret_cast<const uint4*>(x16 + ((int64_t)next * 128 + tid) * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xr[i] = rp[i];
       }
     }
     wait_bar(&bar_m0, ph, status, &s_abort, kErrFcMma);

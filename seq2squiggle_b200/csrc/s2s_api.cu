@@ -31,7 +31,7 @@ struct s2s_engine {
   float* d_f32 = nullptr;   // derived fp32 weights
   __half* d_f16 = nullptr;  // fp16 operand copies (tcgen05 path)
   DevWeights dw{};
-  int64_t batch_chunks = 16384;  // chunks per sub-batch of the tensor-core path (S2S_BATCH_CHUNKS)
+  int64_t batch_chunks = 32768;  // chunks per sub-batch of the tensor-core path (S2S_BATCH_CHUNKS)
   int64_t batch_chunks_f32 = 1024;  // fp32 parity path: its fp32 scratch is 2.6 MB per chunk
   TcState tc{};
 };

@@ -119,7 +119,8 @@ class Engine:
             raise RuntimeError("s2s_workspace_bytes failed")
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
-            self._ws = torch.empty(int(need * 1.05) + 4096, dtype=torch.uint8, device=self.device)
+            # grow geometrically: a reallocation is a cudaFree + cudaMalloc, i.e. a device synchronisation
+            self._ws = torch.empty(int(need * 1.3) + 4096, dtype=torch.uint8, device=self.device)
         return self._ws
 
     def _make_taps(self, n_chunks: int, names) -> Tuple[Optional[_lib.S2STaps], Dict[str, torch.Tensor]]:

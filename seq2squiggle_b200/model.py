@@ -30,6 +30,8 @@ from .signal_io import BLOW5Writer
 
 logger = logging.getLogger("seq2squiggle")
 
+PIPE_CHUNKS = 65536   # chunks per pipeline piece of predict_reads (4 engine sub-batches)
+
 
 class _HParams(dict):
     """``model.hparams`` as Lightning exposes it: attribute and item access."""
@@ -172,7 +174,20 @@ class seq2squiggle:
         is exported as soon as its signal reaches the host (no ``keep_last`` hold-back needed)."""
         if self._pipe is None:
             self._pipe = _ReadPipeline(self)
-        self._pipe.submit(reads, chunk_id_base)
+        # pieces of about PIPE_CHUNKS chunks: the copy / writer stages run one piece behind the compute stage, so the
+        # un-overlapped tail of a run is one piece, not one caller-sized batch
+        k, piece, n = self.engine.k, [], 0
+        base = chunk_id_base
+        for item in reads:
+            piece.append(item)
+            nk = len(item[0]) - k + 1
+            n += (nk + 15) // 16 if nk > 0 else 0
+            if n >= PIPE_CHUNKS:
+                self._pipe.submit(piece, base)
+                base = None if base is None else base + n
+                piece, n = [], 0
+        if piece:
+            self._pipe.submit(piece, base)
 
 
 class _ReadPipeline:
@@ -189,8 +204,22 @@ class _ReadPipeline:
         self.q: "queue.Queue" = queue.Queue(maxsize=4)
         self.err: Optional[BaseException] = None
         self.stats = dict(reads=0, chunks=0, samples=0, h2d_bytes=0, d2h_bytes=0)
+        # pinned staging buffers for the int16 signal are recycled (cudaHostAlloc of ~50 MB per batch costs more than
+        # the copy it serves and synchronises the device)
+        self.free_sig: "queue.Queue" = queue.Queue()
+        self.sig_cap = 0
         self.thread = threading.Thread(target=self._writer_loop, daemon=True)
         self.thread.start()
+
+    def _pinned_sig(self, n: int) -> torch.Tensor:
+        try:
+            buf = self.free_sig.get_nowait()
+        except queue.Empty:
+            buf = None
+        if buf is None or buf.numel() < n:
+            self.sig_cap = max(self.sig_cap, int(1.25 * n) + 1)
+            buf = torch.empty(self.sig_cap, dtype=torch.int16, pin_memory=True)
+        return buf
 
     def submit(self, reads, chunk_id_base=None):
         if self.err:
@@ -222,7 +251,7 @@ class _ReadPipeline:
     def _fetch(self, b):
         b["off_ev"].synchronize()
         n = int(b["off_host"][-1])
-        sig = torch.empty(max(n, 1), dtype=torch.int16, pin_memory=True)
+        sig = self._pinned_sig(max(n, 1))
         with torch.cuda.stream(self.copy):
             sig[:n].copy_(b["raw"][:n], non_blocking=True)
             ev = torch.cuda.Event()
@@ -243,10 +272,11 @@ class _ReadPipeline:
                 off = b["off_host"].numpy()
                 sig = b["sig"].numpy()
                 w = self.m.out_writer
-                if w is not None:
+                if w is not None:      # the views are valid until save() returns (writer plug-point contract)
                     w.signals = OrderedDict((name, sig[off[i]:off[i + 1]]) for i, name in enumerate(b["names"]))
                     w.save()
                     w.signals = []
+                self.free_sig.put(b.pop("sig"))
             except BaseException as exc:  # surfaced on the next submit()/finish()
                 self.err = exc
 
