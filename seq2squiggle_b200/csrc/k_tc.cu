@@ -765,7 +765,8 @@ int tc_init(TcState& s, const DevWeights& w, int device) {
   }
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_qkv_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemQkv));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt));
-  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn2, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn4, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt));
   if (const char* env = getenv("S2S_ATTN_V1")) s.attn_v1 = atoi(env) != 0;
   if (const char* env = getenv("S2S_ATTN_V2")) s.attn_v1 = atoi(env) == 0;
@@ -829,9 +830,16 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* p_out
       // (2.96 vs 2.40 ms per 16384 chunks): with 4-5 busy warps per scheduler the MMA issue warps get too few issue slots
       // and the softmax warps wait for S (profiles/r01_attn4_experiment.txt).
       static const int attn_ver = getenv("S2S_ATTN_VER") ? atoi(getenv("S2S_ATTN_VER")) : 2;
-      if (attn_ver != 4)
-        k_tc_attn2<<<grid2a, kAttn2Threads, smem2a, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags,
-                                                             s.d_status);
+      // S2S_ATTN_BOUND=1: Cauchy-Schwarz reference folded into the S MMA (k_tc_attn2<true>): parity-green, no scaling FFMA
+      // and no row-max pass, but measured no faster (4.76 vs 4.76-4.92 ms per 32768 chunks): the exp pass is bound by the
+      // XU pipe, which also executes the F2FP packs (8 (1 - f) + 1 clk per exponential per scheduler).
+      static const int attn_bound = getenv("S2S_ATTN_BOUND") ? atoi(getenv("S2S_ATTN_BOUND")) : 0;
+      if (attn_ver != 4 && attn_bound)
+        k_tc_attn2<true><<<grid2a, kAttn2Threads, smem2a, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags,
+                                                                   s.d_status);
+      else if (attn_ver != 4)
+        k_tc_attn2<false><<<grid2a, kAttn2Threads, smem2a, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags,
+                                                                    s.d_status);
       else
         k_tc_attn4<<<grid_att, kAttn4Threads, kSmemAtt, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags,
                                                               s.d_status);

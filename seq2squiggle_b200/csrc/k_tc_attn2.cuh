@@ -30,6 +30,39 @@ constexpr int kPolyExp = S2S_POLY_EXP;  // exponentials per 32 computed on the F
 #define S2S_POLY_EXP_H2 4
 #endif
 constexpr int kPolyExpH2 = S2S_POLY_EXP_H2;  // pairs per 16 computed by the packed-fp16 polynomial instead of MUFU
+#ifndef S2S_POLY_BOUND_H2
+#define S2S_POLY_BOUND_H2 8
+#endif
+constexpr int kPolyBoundH2 = S2S_POLY_BOUND_H2;  // the same for the kBound kernel (no scaling FFMAs: more fit)
+
+// kBound exp pass: the accumulator already holds (s - m) c, P = 2^x directly
+__device__ __forceinline__ uint32_t ex2_poly_h2_neg(float x0, float x1) {  // x <= ~0: only the lower clamp
+  const __half2 kLo = __float2half2_rn(-15.0f), kMagic = __float2half2_rn(1551.0f);
+  const __half2 x = __hmax2(__floats2half2_rn(x0, x1), kLo);
+  const __half2 t = __hadd2(x, kMagic);
+  const __half2 f = __hsub2(x, __hsub2(t, kMagic));
+  __half2 p = __hfma2(__float2half2_rn(0.05517167f), f, __float2half2_rn(0.24261113f));
+  p = __hfma2(p, f, __float2half2_rn(0.69326097f));
+  p = __hfma2(p, f, __float2half2_rn(0.99992806f));
+  const uint32_t sc = (*reinterpret_cast<const uint32_t*>(&t) << 10) & 0x7C007C00u;
+  const __half2 r = __hmul2(p, *reinterpret_cast<const __half2*>(&sc));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <int kValid, int kPolyH>
+__device__ __forceinline__ void chunk_exp_store_direct(const uint32_t (&r)[32], uint32_t taddr) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (kPolyH > 0 && 2 * i + 1 < kValid && (i * kPolyH) % 16 < kPolyH) {
+      pk[i] = ex2_poly_h2_neg(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+    } else {
+      const float p0 = 2 * i < kValid ? ex2_approx(__uint_as_float(r[2 * i])) : 0.f;
+      const float p1 = 2 * i + 1 < kValid ? ex2_approx(__uint_as_float(r[2 * i + 1])) : 0.f;
+      pk[i] = pack_half2(p0, p1);
+    }
+  }
+  tmem_st_32x16(taddr, pk);
+}
 
 __device__ __forceinline__ void warp_arrive(uint64_t* bar) {
   __syncwarp();
@@ -46,6 +79,16 @@ struct Ring3 {  // which of the three S/P buffers the next quarter uses, and the
   }
 };
 
+// kBound = true: the softmax reference of a row is an upper bound known BEFORE the scores exist,
+//   m_i = |c q_i| * max_j |k_j|  (Cauchy-Schwarz; c = log2(e)/sqrt(d_k), per head),
+// and it is subtracted by the S MMA itself: every head owns a whole K=16 operand slice, A = [c q_i (8) | -m_i, 0 x 7],
+// B = [k_j (8) | 1, 0 x 7], so the accumulator already holds (s_ij - m_i) c and the exp pass is one MUFU (or the
+// packed polynomial) per score with NO scaling FFMA and no row-max pass: the FMA pipe, which the scaling FFMAs and the
+// polynomial share, is what limits how many exponentials can be taken off the MUFU pipe.  P <= 1 always (no overflow);
+// if the bound is so loose that the probabilities sink towards the fp16 subnormals the row's denominator (ones row
+// of V^T) falls under 2^-9 and the unit is recomputed by the exact kernel, like an overflow in the kBound = false
+// scheme (reference = max of the row's first 32 scores, subtracted in the exp pass).
+template <bool kBound>
 __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_constant__ CUtensorMap tmX,
                                                                const __grid_constant__ CUtensorMap tmWg,
                                                                const float* __restrict__ bias_g, __half* __restrict__ o16,
@@ -58,8 +101,9 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
   __shared__ uint32_t s_tmem;
   __shared__ int s_abort, s_go;
   __shared__ float s_bias[2][96];
+  __shared__ float s_kmax[2][4];       // kBound: max_j |k_j|^2 per head of the unit (double-buffered by unit parity)
   uint8_t* smem = align1024(smem_raw);
-  uint8_t* sXQ = smem;                 // 2 x [128 x 128 B]: X tiles, then Q (bytes [0,64) of each row)
+  uint8_t* sXQ = smem;                 // 2 x [128 x 128 B]: X tiles, then Q (bytes [0,64) of each row; kBound: all 128)
   uint8_t* sK = smem + 2 * kSlab;      // [256 keys x 128 B]  masked K of this head group (4 quarters of 8 KB)
   uint8_t* sV = smem + 4 * kSlab;      // 4 key quarters x [64 rows (4 heads x 16) x 128 B]
   uint8_t* sW = smem + 6 * kSlab;      // [96 x 128 B] weight block of the CTA's head group
@@ -81,8 +125,17 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
   // V^T padding rows are constant: row 8 of every head = ones (softmax denominator), rows 9..15 = 0
   for (int i = tid; i < 2 * kSlab / 16; i += kAttn2Threads) {
     reinterpret_cast<uint4*>(sV)[i] = make_uint4(0u, 0u, 0u, 0u);
-    reinterpret_cast<uint4*>(sK)[i] = make_uint4(0u, 0u, 0u, 0u);  // the masked (zero) half of every K slot never changes
+    // kBound = false: the masked (zero) half of every K slot never changes.  kBound = true: the second half of every
+    // 32-byte slot is the constant (1, 0 x 7) that picks up -m_i from the A operand (16-byte chunk index is odd; the
+    // SW128 swizzle only permutes chunks within a row, so "odd chunk" can be tested on the physical index XOR row).
+    uint32_t w0 = 0u;
+    if (kBound) {
+      const uint32_t row = (uint32_t)i >> 3, phys = (uint32_t)i & 7u;
+      if (((phys ^ (row & 7u)) & 1u) != 0u) w0 = 0x00003C00u;  // fp16 1.0 in element 0
+    }
+    reinterpret_cast<uint4*>(sK)[i] = make_uint4(w0, 0u, 0u, 0u);
   }
+  if (tid < 8) s_kmax[tid >> 2][tid & 3] = 0.f;
   __syncthreads();
   for (int i = tid; i < 4 * 4 * 8; i += kAttn2Threads) {  // (quarter, head, 16-byte chunk of 8 keys)
     const int slab = i >> 5, hh = (i >> 3) & 3, ck = i & 7;
@@ -160,7 +213,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
       // S for quarter j: A = Q slice of (tile, head pair), B = masked-K slot of the head, rows of key quarter q
       auto issue_S = [&](int j, uint32_t buf) {
         const int M = j >> 2, q = j & 3, hh = M >> 1, tile = M & 1;
-        umma_f16_ss(tmem + 64 * buf, dXQ + (uint64_t)((tile * kSlab + (hh >> 1) * 32) >> 4),
+        umma_f16_ss(tmem + 64 * buf, dXQ + (uint64_t)((tile * kSlab + (kBound ? hh : (hh >> 1)) * 32) >> 4),
                     dK + (uint64_t)((q * 8192 + hh * 32) >> 4), idesc_s, 0);
         umma_commit_a(BAR(B_S + buf));
       };
@@ -227,9 +280,10 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
       wait_a(BAR(B_QKV), upar, kErrAttS);
       tcgen05_fence_after();
       PHASE(1);
-      {  // QKV epilogue: accumulators -> fp16 operands in shared memory.  Only Q needs its bias here: the K bias adds a
-         // per-row constant q.b_k to every score (softmax-invariant), and the V bias is added once to the normalised
-         // output (sum_j p_j (v_j + b_v) = sum_j p_j v_j + b_v).  The zero halves of the masked K slots are static.
+      if constexpr (!kBound) {
+        // QKV epilogue: accumulators -> fp16 operands in shared memory.  Only Q needs its bias here: the K bias adds a
+        // per-row constant q.b_k to every score (softmax-invariant), and the V bias is added once to the normalised
+        // output (sum_j p_j (v_j + b_v) = sum_j p_j v_j + b_v).  The zero halves of the masked K slots are static.
         const float* bq = s_bias[g];
 #pragma unroll
         for (int tile = 0; tile < 2; ++tile) {
@@ -259,6 +313,69 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
             for (int d = 0; d < 8; ++d)
               *reinterpret_cast<__half*>(vslab + sw128_offset(hh * 16 + d, ck)) = __float2half_rn(__uint_as_float(rv[8 * hh + d]));
         }
+      } else {
+        // kBound epilogue, two passes.  Pass 1 (both tiles): K (first half of each head's 32-byte slot; no bias, see
+        // above) and V^T to shared memory, and max_j |k_j|^2 per head over the chunk's 256 keys (warp max, then one
+        // shared atomicMax per warp; non-negative floats order like their bit patterns).
+        const uint32_t kp = upar;
+#pragma unroll
+        for (int tile = 0; tile < 2; ++tile) {
+          const int t = tile * 128 + tid;
+          uint32_t rk[32], rv[32];
+          tmem_ld_32x32(lane_addr + tile * 128 + 32, rk);
+          tmem_ld_32x32(lane_addr + tile * 128 + 64, rv);
+          tmem_wait_ld();
+#pragma unroll
+          for (int hh = 0; hh < 4; ++hh) {
+            uint32_t pk[4];
+            float n2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float k0 = __uint_as_float(rk[8 * hh + 2 * i]), k1 = __uint_as_float(rk[8 * hh + 2 * i + 1]);
+              pk[i] = pack_half2(k0, k1);
+              n2 = fmaf(k0, k0, fmaf(k1, k1, n2));
+            }
+            *reinterpret_cast<uint4*>(sK + sw128_offset(t, 2 * hh)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(n2));
+            if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(&s_kmax[kp][hh]), wmax);
+          }
+          uint8_t* vslab = sV + (t >> 6) * 8192 + (t & 7) * 2;
+          const uint32_t ck = (t & 63) >> 3;
+#pragma unroll
+          for (int hh = 0; hh < 4; ++hh)
+#pragma unroll
+            for (int d = 0; d < 8; ++d)
+              *reinterpret_cast<__half*>(vslab + sw128_offset(hh * 16 + d, ck)) = __float2half_rn(__uint_as_float(rv[8 * hh + d]));
+        }
+        if (tid < 4) s_kmax[kp ^ 1u][tid] = 0.f;             // the other parity's slots: free since the previous unit
+        asm volatile("bar.sync 1, 128;" ::: "memory");       // the four softmax warps only (warp 4 never joins)
+        // Pass 2: Q scaled by c = log2(e)/sqrt(d_k), and -m_i = -|c q_i| max_j|k_j| in element 8 of the head's slice
+        const float* bq = s_bias[g];
+        float kmax2[4];
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) kmax2[hh] = s_kmax[kp][hh] * 1.002f;  // fp16 rounding of q and k: keep it a bound
+#pragma unroll
+        for (int tile = 0; tile < 2; ++tile) {
+          uint32_t rq[32];
+          tmem_ld_32x32(lane_addr + tile * 128, rq);
+          tmem_wait_ld();
+#pragma unroll
+          for (int hh = 0; hh < 4; ++hh) {
+            uint32_t pq[4];
+            float n2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float q0 = (__uint_as_float(rq[8 * hh + 2 * i]) + bq[8 * hh + 2 * i]) * kScale;
+              const float q1 = (__uint_as_float(rq[8 * hh + 2 * i + 1]) + bq[8 * hh + 2 * i + 1]) * kScale;
+              pq[i] = pack_half2(q0, q1);
+              n2 = fmaf(q0, q0, fmaf(q1, q1, n2));
+            }
+            const float m = sqrtf(n2 * kmax2[hh]);
+            *reinterpret_cast<uint4*>(sXQ + tile * kSlab + sw128_offset(tid, 2 * hh)) = make_uint4(pq[0], pq[1], pq[2], pq[3]);
+            *reinterpret_cast<uint4*>(sXQ + tile * kSlab + sw128_offset(tid, 2 * hh + 1)) =
+                make_uint4(pack_half2(-m, 0.f), 0u, 0u, 0u);
+          }
+        }
       }
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
       tcgen05_fence_before();
@@ -280,6 +397,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
         warp_arrive_a(BAR(B_OF + acc_i));
         const float den = __uint_as_float(o[8]);  // sum of the rounded probabilities (ones row of V^T)
         overflow |= !(den < 1e30f);                // inf / NaN: some P overflowed fp16 -> exact kernel redoes the unit
+        if (kBound) overflow |= den < 0.001953125f;  // loose bound: probabilities near the fp16 subnormals
         const float inv = 1.0f / den;
         const float* bv = s_bias[g] + 64 + 8 * hh;
         const int64_t row = (int64_t)chunk * 256 + tile * 128 + tid;
@@ -311,9 +429,10 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
           const uint32_t col = lane_addr + 64 * cb, ncol = lane_addr + 64 * nb;
           tmem_wait_ld();
           if (q == 1 && M > 0) take_O_finish(M - 1);  // its tcgen05.ld was issued in the middle of the previous quarter
-          if (q == 0) mneg = -chunk_max<32>(ra, -INFINITY) * kScale;  // the row's reference: max of its first 32 scores
+          if (!kBound && q == 0) mneg = -chunk_max<32>(ra, -INFINITY) * kScale;  // reference: max of the first 32 scores
           PHASE(4);
-          chunk_exp_store_mixed<32, kPolyExp, kPolyExpH2>(ra, kScale, mneg, col);
+          if (kBound) chunk_exp_store_direct<32, kPolyBoundH2>(ra, col);
+          else chunk_exp_store_mixed<32, kPolyExp, kPolyExpH2>(ra, kScale, mneg, col);
           if (q == 0 && M > 0) {  // O of the previous (head, tile): its last P.V was issued most of a quarter ago
             take_O_issue();
             tmem_ld_32x16(lane_addr + kOaccCol + 16 * ((M - 1) & 1), o);
@@ -326,8 +445,13 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
               tmem_ld_32x32(ncol, ra);
             }
           }
-          if (q == 3) chunk_exp_store_mixed<S2S_L_DEC - 224, kPolyExp, kPolyExpH2>(rb, kScale, mneg, col + 16);
-          else chunk_exp_store_mixed<32, kPolyExp, kPolyExpH2>(rb, kScale, mneg, col + 16);
+          if (kBound) {
+            if (q == 3) chunk_exp_store_direct<S2S_L_DEC - 224, kPolyBoundH2>(rb, col + 16);
+            else chunk_exp_store_direct<32, kPolyBoundH2>(rb, col + 16);
+          } else {
+            if (q == 3) chunk_exp_store_mixed<S2S_L_DEC - 224, kPolyExp, kPolyExpH2>(rb, kScale, mneg, col + 16);
+            else chunk_exp_store_mixed<32, kPolyExp, kPolyExpH2>(rb, kScale, mneg, col + 16);
+          }
           PHASE(5);
           if (has_next) {
             if (!ready) {
