@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(256) k_embed(const float* __restrict__ src_t, 
                                                const uint8_t* __restrict__ bases, const int64_t* __restrict__ chunk_base,
                                                const int32_t* __restrict__ chunk_nk, const int8_t* __restrict__ codes,
                                                int64_t n_chunks, float* __restrict__ emb_out, float* __restrict__ x_enc,
-                                               __half* __restrict__ x_enc16) {
+                                               __half* __restrict__ x_enc16, const int* __restrict__ run_if) {
+  if (run_if != nullptr && *run_if == 0) return;
   __shared__ int8_t s_code[S2S_L_ENC][12];
   __shared__ __align__(16) float s_e1[S2S_L_ENC][S2S_D];
   const int64_t c = blockIdx.x;
@@ -108,10 +109,87 @@ int launch_chunk_map(const int64_t* read_offsets, const int64_t* chunk_offsets, 
 }
 
 int launch_embed(const DevWeights& w, const uint8_t* bases, const int64_t* chunk_base, const int32_t* chunk_nk,
-                 const int8_t* codes, int64_t n_chunks, float* emb_out, float* x_enc, __half* x_enc16, cudaStream_t st) {
+                 const int8_t* codes, int64_t n_chunks, float* emb_out, float* x_enc, __half* x_enc16, cudaStream_t st,
+                 const int* run_if) {
   if (n_chunks == 0) return 0;
   k_embed<<<(unsigned)n_chunks, 256, 0, st>>>(w.src_t, w.src_b, w.pre_t, w.pre_b, w.enc_pos, w.cfg.seq_kmer, bases,
-                                              chunk_base, chunk_nk, codes, n_chunks, emb_out, x_enc, x_enc16);
+                                              chunk_base, chunk_nk, codes, n_chunks, emb_out, x_enc, x_enc16, run_if);
+  S2S_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- per-k-mer tables ------------------------------------------------------------------------------
+__global__ void k_all_kmer_codes(int k, int64_t n_rows, int64_t n_kmers, int8_t* __restrict__ codes) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  int64_t v = r;
+  for (int i = k - 1; i >= 0; --i) {  // most significant letter first
+    codes[r * k + i] = r < n_kmers ? (int8_t)(1 + (v & 3)) : (int8_t)0;
+    v >>= 2;
+  }
+}
+
+int launch_all_kmer_codes(int k, int64_t n_rows, int8_t* codes, cudaStream_t st) {
+  k_all_kmer_codes<<<(unsigned)ceil_div(n_rows, 256), 256, 0, st>>>(k, n_rows, (int64_t)1 << (2 * k), codes);
+  S2S_LAUNCH_CHECK();
+  return 0;
+}
+
+// One CTA (256 threads) per chunk like k_embed: thread = (k-mer j = tid/16, 4 channels cg = tid%16).  The k-mer's
+// table index is the base-4 number of its letters (A,C,G,T = 0..3); "_"*k is entry 4^k; anything else (a letter
+// outside "_ACGT", or "_" mixed with bases, which only hand-made code tensors can contain) is not in the table.
+__global__ void __launch_bounds__(256) k_embed_lookup(const float* __restrict__ tab_emb, int64_t n_kmers, int* __restrict__ flag,
+                                                      const float* __restrict__ enc_pos, int k,
+                                                      const uint8_t* __restrict__ bases, const int64_t* __restrict__ chunk_base,
+                                                      const int32_t* __restrict__ chunk_nk, const int8_t* __restrict__ codes,
+                                                      float* __restrict__ emb_out, float* __restrict__ x_enc,
+                                                      __half* __restrict__ x_enc16, int32_t* __restrict__ kidx) {
+  __shared__ int32_t s_idx[S2S_L_ENC];
+  const int64_t c = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (tid < S2S_L_ENC) {
+    const int j = tid;
+    int64_t idx = 0;
+    int n_pad = 0;
+    bool bad = false;
+    const bool is_pad_kmer = codes == nullptr && j >= chunk_nk[c];
+    for (int i = 0; i < k; ++i) {
+      int code;
+      if (codes != nullptr) code = codes[(c * S2S_L_ENC + j) * k + i];
+      else code = is_pad_kmer ? 0 : letter_code(bases[chunk_base[c] + j + i]);
+      if (code < 0) bad = true;
+      else if (code == 0) ++n_pad;
+      else idx = idx * 4 + (code - 1);
+    }
+    int32_t out;
+    if (bad || (n_pad != 0 && n_pad != k)) out = -1;
+    else out = n_pad == k ? (int32_t)n_kmers : (int32_t)idx;
+    if (out < 0) atomicOr(flag, 1);
+    s_idx[j] = out;
+    kidx[c * S2S_L_ENC + j] = out;
+  }
+  __syncthreads();
+  const int j = tid >> 4, cg = tid & 15;
+  const int32_t idx = s_idx[j];
+  if (idx < 0) return;  // the fallback launches recompute the whole sub-batch
+  float4 o = *reinterpret_cast<const float4*>(tab_emb + (size_t)idx * S2S_D + 4 * cg);
+  const size_t off = ((size_t)c * S2S_L_ENC + j) * S2S_D + 4 * cg;
+  *reinterpret_cast<float4*>(emb_out + off) = o;
+  float4 p = *reinterpret_cast<const float4*>(enc_pos + j * S2S_D + 4 * cg);
+  o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+  *reinterpret_cast<float4*>(x_enc + off) = o;
+  if (x_enc16) {
+    __half2 a = __floats2half2_rn(o.x, o.y), b = __floats2half2_rn(o.z, o.w);
+    *reinterpret_cast<uint2*>(x_enc16 + off) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+  }
+}
+
+int launch_embed_lookup(const DevWeights& w, const KmerTables& tab, const uint8_t* bases, const int64_t* chunk_base,
+                        const int32_t* chunk_nk, const int8_t* codes, int64_t n_chunks, float* emb_out, float* x_enc,
+                        __half* x_enc16, int32_t* kidx, cudaStream_t st) {
+  if (n_chunks == 0) return 0;
+  k_embed_lookup<<<(unsigned)n_chunks, 256, 0, st>>>(tab.emb, tab.n_kmers, tab.flag, w.enc_pos, w.cfg.seq_kmer, bases,
+                                                     chunk_base, chunk_nk, codes, emb_out, x_enc, x_enc16, kidx);
   S2S_LAUNCH_CHECK();
   return 0;
 }

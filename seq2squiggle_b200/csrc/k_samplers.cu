@@ -41,11 +41,57 @@ __device__ float sample_standard_gamma(const Philox& ph, uint64_t idx, float alp
   return boost * d;  // unreachable in practice (acceptance > 95% per attempt)
 }
 
+// clamps, duration draw and rounding of one k-mer given its (conc, rate, sigma)
+__device__ __forceinline__ void finish_sampler(int64_t row, float conc, float rate, float sg, const s2s_run_opts& o,
+                                               float* __restrict__ sigma, int32_t* __restrict__ dur_int,
+                                               float* __restrict__ conc_tap, float* __restrict__ rate_tap,
+                                               float* __restrict__ dur_float_tap) {
+  sigma[row] = sg;
+  if (conc_tap) conc_tap[row] = conc;
+  if (rate_tap) rate_tap[row] = rate;
+  const uint64_t gidx = o.chunk_id_base * S2S_L_ENC + (uint64_t)row;
+  Philox ph(o.seed);
+  float d;
+  if (o.duration_mode == S2S_DUR_SAMPLER) {
+    d = sample_standard_gamma(ph, gidx, conc) / rate;
+    d = fmaxf(d, 1.17549435e-38f);  // torch.distributions.Gamma.rsample clamps to finfo.tiny
+    d = fmaxf(d, 1.0f);             // modules.py:223
+    d = fmaxf(d, o.min_duration);   // modules.py:414
+  } else if (o.duration_mode == S2S_DUR_NORMAL) {
+    uint4 r = ph((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, kStreamDwellNormal);
+    d = o.dwell_mean + o.dwell_std * box_muller(r.x, r.y).x;
+    d = fmaxf(d, o.min_duration);   // modules.py:430
+  } else {
+    d = o.dwell_mean;               // modules.py:420: no clamp in the constant branch
+  }
+  if (dur_float_tap) dur_float_tap[row] = d;
+  dur_int[row] = (int32_t)rintf(d);  // torch.round: half to even
+}
+
+__global__ void __launch_bounds__(256) k_sampler_lookup(const float4* __restrict__ tab_smp, const int32_t* __restrict__ kidx,
+                                                        int64_t n_kmers, s2s_run_opts o, float* __restrict__ sigma,
+                                                        int32_t* __restrict__ dur_int, float* __restrict__ conc_tap,
+                                                        float* __restrict__ rate_tap, float* __restrict__ dur_float_tap) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_kmers) return;
+  const int32_t idx = kidx[row];
+  if (idx < 0) return;
+  const float4 t = tab_smp[idx];
+  finish_sampler(row, t.x, t.y, t.z, o, sigma, dur_int, conc_tap, rate_tap, dur_float_tap);
+}
+
+__global__ void k_pack_smp_table(const float* __restrict__ conc, const float* __restrict__ rate,
+                                 const float* __restrict__ sigma, int64_t n, float4* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_float4(conc[i], rate[i], sigma[i], 0.f);
+}
+
 __global__ void __launch_bounds__(256) k_sampler_heads(const float* __restrict__ h3, const float* __restrict__ w3,
                                                        const float* __restrict__ b3, int64_t n_kmers, s2s_run_opts o,
                                                        float* __restrict__ sigma, int32_t* __restrict__ dur_int,
                                                        float* __restrict__ conc_tap, float* __restrict__ rate_tap,
-                                                       float* __restrict__ dur_float_tap) {
+                                                       float* __restrict__ dur_float_tap, const int* __restrict__ run_if) {
+  if (run_if != nullptr && *run_if == 0) return;
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t row0 = warp_global * 32;
@@ -69,34 +115,32 @@ __global__ void __launch_bounds__(256) k_sampler_heads(const float* __restrict__
   const float conc = fmaxf(softplus_torch(mine[0] + b3[0]), 1e-8f);
   const float rate = fmaxf(softplus_torch(mine[1] + b3[1]), 1e-8f);
   const float sg = softplus_torch(mine[2] + b3[2]);
-  sigma[row] = sg;
-  if (conc_tap) conc_tap[row] = conc;
-  if (rate_tap) rate_tap[row] = rate;
-  const uint64_t gidx = o.chunk_id_base * S2S_L_ENC + (uint64_t)row;
-  Philox ph(o.seed);
-  float d;
-  if (o.duration_mode == S2S_DUR_SAMPLER) {
-    d = sample_standard_gamma(ph, gidx, conc) / rate;
-    d = fmaxf(d, 1.17549435e-38f);  // torch.distributions.Gamma.rsample clamps to finfo.tiny
-    d = fmaxf(d, 1.0f);             // modules.py:223
-    d = fmaxf(d, o.min_duration);   // modules.py:414
-  } else if (o.duration_mode == S2S_DUR_NORMAL) {
-    uint4 r = ph((uint32_t)gidx, (uint32_t)(gidx >> 32), 0u, kStreamDwellNormal);
-    d = o.dwell_mean + o.dwell_std * box_muller(r.x, r.y).x;
-    d = fmaxf(d, o.min_duration);   // modules.py:430
-  } else {
-    d = o.dwell_mean;               // modules.py:420: no clamp in the constant branch
-  }
-  if (dur_float_tap) dur_float_tap[row] = d;
-  dur_int[row] = (int32_t)rintf(d);  // torch.round: half to even
+  finish_sampler(row, conc, rate, sg, o, sigma, dur_int, conc_tap, rate_tap, dur_float_tap);
 }
 
 int launch_sampler_heads(const DevWeights& w, const float* h3, int64_t n_kmers, const s2s_run_opts& o, float* sigma,
-                         int32_t* dur_int, float* conc_tap, float* rate_tap, float* dur_float_tap, cudaStream_t st) {
+                         int32_t* dur_int, float* conc_tap, float* rate_tap, float* dur_float_tap, cudaStream_t st,
+                         const int* run_if) {
   if (n_kmers == 0) return 0;
   int64_t warps = ceil_div(n_kmers, 32);
   k_sampler_heads<<<(unsigned)ceil_div(warps, 8), 256, 0, st>>>(h3, w.smp3_w, w.smp3_b, n_kmers, o, sigma, dur_int,
-                                                                conc_tap, rate_tap, dur_float_tap);
+                                                                conc_tap, rate_tap, dur_float_tap, run_if);
+  S2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_sampler_lookup(const KmerTables& tab, const int32_t* kidx, int64_t n_kmers, const s2s_run_opts& o,
+                          float* sigma, int32_t* dur_int, float* conc_tap, float* rate_tap, float* dur_float_tap,
+                          cudaStream_t st) {
+  if (n_kmers == 0) return 0;
+  k_sampler_lookup<<<(unsigned)ceil_div(n_kmers, 256), 256, 0, st>>>(tab.smp, kidx, n_kmers, o, sigma, dur_int, conc_tap,
+                                                                     rate_tap, dur_float_tap);
+  S2S_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_pack_smp_table(const float* conc, const float* rate, const float* sigma, int64_t n, float4* out, cudaStream_t st) {
+  k_pack_smp_table<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(conc, rate, sigma, n, out);
   S2S_LAUNCH_CHECK();
   return 0;
 }

@@ -14,7 +14,8 @@ template <int K, int N, int EPI>
 __global__ void __launch_bounds__(256) k_linear_f32(const float* __restrict__ X, const float* __restrict__ Wt,
                                                     const float* __restrict__ bias, const float* __restrict__ R,
                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                    float* __restrict__ Y, int64_t M) {
+                                                    float* __restrict__ Y, int64_t M, const int* __restrict__ run_if) {
+  if (run_if != nullptr && *run_if == 0) return;  // fallback launch of the k-mer table path: nothing to recompute
   constexpr int TM = 32, NJ = N / 64;
   static_assert(N % 64 == 0 && K % 4 == 0, "shape");
   static_assert(EPI != EPI_BIAS_RES_LN || N == 64, "LayerNorm epilogue needs the whole row in one tile");
@@ -100,20 +101,20 @@ __global__ void __launch_bounds__(256) k_linear_f32(const float* __restrict__ X,
 
 template <int K, int N, int EPI>
 static int launch_linear_t(const float* X, const float* Wt, const float* b, const float* R, const float* g,
-                           const float* beta, float* Y, int64_t M, cudaStream_t st) {
+                           const float* beta, float* Y, int64_t M, cudaStream_t st, const int* run_if) {
   if (M == 0) return 0;
-  k_linear_f32<K, N, EPI><<<(unsigned)ceil_div(M, 32), 256, 0, st>>>(X, Wt, b, R, g, beta, Y, M);
+  k_linear_f32<K, N, EPI><<<(unsigned)ceil_div(M, 32), 256, 0, st>>>(X, Wt, b, R, g, beta, Y, M, run_if);
   S2S_LAUNCH_CHECK();
   return 0;
 }
 
 int launch_linear_f32(const float* X, const float* Wt, const float* b, const float* R, const float* g,
-                      const float* beta, float* Y, int64_t M, int K, int N, int epi, cudaStream_t st) {
-  if (K == 64 && N == 192 && epi == EPI_BIAS) return launch_linear_t<64, 192, EPI_BIAS>(X, Wt, b, R, g, beta, Y, M, st);
-  if (K == 64 && N == 192 && epi == EPI_BIAS_RELU) return launch_linear_t<64, 192, EPI_BIAS_RELU>(X, Wt, b, R, g, beta, Y, M, st);
-  if (K == 64 && N == 256 && epi == EPI_BIAS_RELU) return launch_linear_t<64, 256, EPI_BIAS_RELU>(X, Wt, b, R, g, beta, Y, M, st);
-  if (K == 64 && N == 64 && epi == EPI_BIAS_RES_LN) return launch_linear_t<64, 64, EPI_BIAS_RES_LN>(X, Wt, b, R, g, beta, Y, M, st);
-  if (K == 256 && N == 64 && epi == EPI_BIAS_RES_LN) return launch_linear_t<256, 64, EPI_BIAS_RES_LN>(X, Wt, b, R, g, beta, Y, M, st);
+                      const float* beta, float* Y, int64_t M, int K, int N, int epi, cudaStream_t st, const int* run_if) {
+  if (K == 64 && N == 192 && epi == EPI_BIAS) return launch_linear_t<64, 192, EPI_BIAS>(X, Wt, b, R, g, beta, Y, M, st, run_if);
+  if (K == 64 && N == 192 && epi == EPI_BIAS_RELU) return launch_linear_t<64, 192, EPI_BIAS_RELU>(X, Wt, b, R, g, beta, Y, M, st, run_if);
+  if (K == 64 && N == 256 && epi == EPI_BIAS_RELU) return launch_linear_t<64, 256, EPI_BIAS_RELU>(X, Wt, b, R, g, beta, Y, M, st, run_if);
+  if (K == 64 && N == 64 && epi == EPI_BIAS_RES_LN) return launch_linear_t<64, 64, EPI_BIAS_RES_LN>(X, Wt, b, R, g, beta, Y, M, st, run_if);
+  if (K == 256 && N == 64 && epi == EPI_BIAS_RES_LN) return launch_linear_t<256, 64, EPI_BIAS_RES_LN>(X, Wt, b, R, g, beta, Y, M, st, run_if);
   set_error("launch_linear_f32: unsupported shape K=%d N=%d epi=%d", K, N, epi);
   return -1;
 }

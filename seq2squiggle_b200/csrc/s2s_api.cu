@@ -3,6 +3,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <string>
 #include <vector>
 
 #include "s2s_kernels.h"
@@ -34,6 +35,11 @@ struct s2s_engine {
   int64_t batch_chunks = 32768;  // chunks per sub-batch of the tensor-core path (S2S_BATCH_CHUNKS)
   int64_t batch_chunks_f32 = 1024;  // fp32 parity path: its fp32 scratch is 2.6 MB per chunk
   TcState tc{};
+  // per-k-mer tables of the front end (S2S_KMER_TABLES=0 disables them): built by s2s_create for k <= 9
+  KmerTables tab{};
+  float* d_tab_emb = nullptr;
+  float4* d_tab_smp = nullptr;
+  int* d_tab_flag = nullptr;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -155,7 +161,7 @@ struct Workspace {
   int64_t compact_bytes;
   // per sub-batch
   float *emb, *xe, *qkv_e, *att_e, *ye, *he, *h3, *sigma;
-  int32_t *dur, *total;
+  int32_t *dur, *total, *kidx;
   float *xd, *qkv_d, *att_d, *yd, *hd, *sigma_ext, *p_rows;
   TcBuffers tcb;
 };
@@ -180,6 +186,7 @@ int64_t carve(Workspace& w, void* base, const s2s_engine* h, int64_t n_chunks, i
   w.h3 = cv.take<float>(me * 192);
   w.sigma = cv.take<float>(me);
   w.dur = cv.take<int32_t>(me);
+  w.kidx = cv.take<int32_t>(me);
   w.total = cv.take<int32_t>(bc);
   w.xd = cv.take<float>(md32 * 64);
   w.qkv_d = cv.take<float>(md32 * 192);
@@ -222,9 +229,19 @@ int run_pipeline(s2s_engine* h, const uint8_t* bases, const int8_t* codes, const
     const int64_t me = bc * S2S_L_ENC;
     s2s_run_opts o = opts;
     o.chunk_id_base = opts.chunk_id_base + (uint64_t)c0;
-    // K-A
+    // K-A: by per-k-mer table when there is one; the direct kernels then only run (device-side flag) for a sub-batch
+    // that contains a k-mer outside the table, and recompute that whole sub-batch with identical arithmetic
+    const bool use_tab = h->tab.emb != nullptr;
+    const int* run_if = use_tab ? h->tab.flag : nullptr;
+    if (use_tab) {
+      S2S_CUDA_OK(cudaMemsetAsync(h->tab.flag, 0, sizeof(int), st));
+      if (launch_embed_lookup(dw, h->tab, bases, bases ? w.chunk_base + c0 : nullptr, bases ? w.chunk_nk + c0 : nullptr,
+                              codes ? codes + c0 * S2S_L_ENC * k : nullptr, bc, w.emb, w.xe,
+                              tc_path ? w.tcb.xe16 : nullptr, w.kidx, st)) return -1;
+    }
     if (launch_embed(dw, bases, bases ? w.chunk_base + c0 : nullptr, bases ? w.chunk_nk + c0 : nullptr,
-                     codes ? codes + c0 * S2S_L_ENC * k : nullptr, bc, w.emb, w.xe, tc_path ? w.tcb.xe16 : nullptr, st))
+                     codes ? codes + c0 * S2S_L_ENC * k : nullptr, bc, w.emb, w.xe, tc_path ? w.tcb.xe16 : nullptr, st,
+                     run_if))
       return -1;
     // encoder (modules.py:82-87)
     if (tc_path) {
@@ -234,11 +251,14 @@ int run_pipeline(s2s_engine* h, const uint8_t* bases, const int8_t* codes, const
         if (fft_block_f32(dw.enc[l], w.xe, w.ye, w.qkv_e, w.att_e, w.he, bc, S2S_L_ENC, S2S_L_ENC, st)) return -1;
     }
     // samplers (K-C)
-    if (launch_linear_f32(w.emb, dw.smp0_t, dw.smp0_b, nullptr, nullptr, nullptr, w.h3, me, 64, 192, EPI_BIAS_RELU, st))
+    float* conc_tap = taps && taps->conc_dev ? taps->conc_dev + c0 * 16 : nullptr;
+    float* rate_tap = taps && taps->rate_dev ? taps->rate_dev + c0 * 16 : nullptr;
+    float* durf_tap = taps && taps->dur_float_dev ? taps->dur_float_dev + c0 * 16 : nullptr;
+    if (use_tab && launch_sampler_lookup(h->tab, w.kidx, me, o, w.sigma, w.dur, conc_tap, rate_tap, durf_tap, st)) return -1;
+    if (launch_linear_f32(w.emb, dw.smp0_t, dw.smp0_b, nullptr, nullptr, nullptr, w.h3, me, 64, 192, EPI_BIAS_RELU, st,
+                          run_if))
       return -1;
-    if (launch_sampler_heads(dw, w.h3, me, o, w.sigma, w.dur, taps && taps->conc_dev ? taps->conc_dev + c0 * 16 : nullptr,
-                             taps && taps->rate_dev ? taps->rate_dev + c0 * 16 : nullptr,
-                             taps && taps->dur_float_dev ? taps->dur_float_dev + c0 * 16 : nullptr, st)) return -1;
+    if (launch_sampler_heads(dw, w.h3, me, o, w.sigma, w.dur, conc_tap, rate_tap, durf_tap, st, run_if)) return -1;
     // K-D
     // fp32 path: fp32 residual stream xd; tensor-core path: the fp16 stream x16 is the only copy
     if (launch_length_regulate(w.xe, w.sigma, w.dur, bc, dw.dec_pos, tc_path ? nullptr : w.xd, tc_path ? w.tcb.x16 : nullptr, S2S_L_DEC_PAD,
@@ -269,6 +289,48 @@ int run_pipeline(s2s_engine* h, const uint8_t* bases, const int8_t* codes, const
     }
     if (taps && tap_copy(taps->pa_dev ? taps->pa_dev + c0 * S2S_L_DEC : nullptr, pa_b, bc * S2S_L_DEC * 4, st)) return -1;
   }
+  return 0;
+}
+
+// emb_out, conc, rate, sigma of every k-mer (and of the "_"*k padding k-mer), computed ONCE with the same kernels the
+// direct path runs per row (k_embed on letter codes, the first sampler layers, the sampler heads), so a looked-up value
+// is bit-identical to a recomputed one.  k = 9: 262,145 entries, 67 MB + 4 MB of HBM, ~1 ms to build.
+int build_kmer_tables(s2s_engine* h) {
+  const int k = h->cfg.seq_kmer;
+  const int64_t nk = (int64_t)1 << (2 * k), rows = align_up(nk + 1, S2S_L_ENC), chunks = rows / S2S_L_ENC;
+  int8_t* codes = nullptr;
+  float *xe = nullptr, *h3 = nullptr, *vals = nullptr;
+  int32_t* dur = nullptr;
+  auto fail = [&](const char* what) {
+    const std::string msg(what);  // `what` may be g_err itself
+    set_error("s2s_create: k-mer tables: %s", msg.c_str());
+    cudaFree(codes); cudaFree(xe); cudaFree(h3); cudaFree(vals); cudaFree(dur);
+    return -1;
+  };
+  if (cudaMalloc(&h->d_tab_emb, rows * 64 * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&h->d_tab_smp, rows * sizeof(float4)) != cudaSuccess ||
+      cudaMalloc(&h->d_tab_flag, sizeof(int)) != cudaSuccess || cudaMalloc(&codes, rows * k) != cudaSuccess ||
+      cudaMalloc(&xe, rows * 64 * sizeof(float)) != cudaSuccess || cudaMalloc(&h3, rows * 192 * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&vals, rows * 3 * sizeof(float)) != cudaSuccess || cudaMalloc(&dur, rows * sizeof(int32_t)) != cudaSuccess)
+    return fail("cudaMalloc failed");
+  cudaStream_t st = nullptr;
+  s2s_run_opts o{};
+  o.duration_mode = S2S_DUR_CONSTANT;  // only conc / rate / sigma are kept; no draw is made
+  o.dwell_mean = 1.f;
+  if (launch_all_kmer_codes(k, rows, codes, st) ||
+      launch_embed(h->dw, nullptr, nullptr, nullptr, codes, chunks, h->d_tab_emb, xe, nullptr, st) ||
+      launch_linear_f32(h->d_tab_emb, h->dw.smp0_t, h->dw.smp0_b, nullptr, nullptr, nullptr, h3, rows, 64, 192,
+                        EPI_BIAS_RELU, st) ||
+      launch_sampler_heads(h->dw, h3, rows, o, vals + 2 * rows, dur, vals, vals + rows, nullptr, st) ||
+      launch_pack_smp_table(vals, vals + rows, vals + 2 * rows, rows, h->d_tab_smp, st))
+    return fail(g_err);
+  if (cudaDeviceSynchronize() != cudaSuccess) return fail("kernel failure");
+  cudaMemset(h->d_tab_flag, 0, sizeof(int));
+  cudaFree(codes); cudaFree(xe); cudaFree(h3); cudaFree(vals); cudaFree(dur);
+  h->tab.emb = h->d_tab_emb;
+  h->tab.smp = h->d_tab_smp;
+  h->tab.n_kmers = nk;
+  h->tab.flag = h->d_tab_flag;
   return 0;
 }
 
@@ -380,6 +442,11 @@ int s2s_create(const float* weights_host, int64_t n_weights, const s2s_config* c
     s2s_destroy(h);
     return -1;
   }
+  const char* tab_env = getenv("S2S_KMER_TABLES");
+  if (cfg->seq_kmer <= 9 && !(tab_env && atoi(tab_env) == 0) && build_kmer_tables(h)) {
+    s2s_destroy(h);
+    return -1;
+  }
   *out = h;
   return 0;
 }
@@ -389,6 +456,9 @@ void s2s_destroy(s2s_handle h) {
   tc_destroy(h->tc);
   if (h->d_f32) cudaFree(h->d_f32);
   if (h->d_f16) cudaFree(h->d_f16);
+  if (h->d_tab_emb) cudaFree(h->d_tab_emb);
+  if (h->d_tab_smp) cudaFree(h->d_tab_smp);
+  if (h->d_tab_flag) cudaFree(h->d_tab_flag);
   delete h;
 }
 

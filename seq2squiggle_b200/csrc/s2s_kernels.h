@@ -38,14 +38,34 @@ struct DevWeights {
 int launch_chunk_map(const int64_t* read_offsets, const int64_t* chunk_offsets, int64_t n_reads, int64_t n_chunks,
                      int32_t k, int32_t* chunk_read, int64_t* chunk_base, int32_t* chunk_nk, cudaStream_t st);
 // Tokenise (bases or codes) + src_emb + ReLU + prenet + ReLU -> emb_out; x_enc = emb_out + pos.
+// run_if (here and below): optional device flag; the launch is a no-op when *run_if == 0 (fallback launches of the
+// k-mer table path, which only have work when a sub-batch contains letters outside "_ACGT").
 int launch_embed(const DevWeights& w, const uint8_t* bases, const int64_t* chunk_base, const int32_t* chunk_nk,
-                 const int8_t* codes, int64_t n_chunks, float* emb_out, float* x_enc, __half* x_enc16, cudaStream_t st);
+                 const int8_t* codes, int64_t n_chunks, float* emb_out, float* x_enc, __half* x_enc16, cudaStream_t st,
+                 const int* run_if = nullptr);
+
+// Per-k-mer tables: emb_out, conc, rate and sigma are functions of ONE k-mer (modules.py:70-78,
+// 216-219, 276), so they are computed once per checkpoint for all 4^k k-mers plus the "_"*k padding k-mer by the
+// kernels above and looked up afterwards: bit-identical values, no per-row GEMMs in the front end.
+struct KmerTables {
+  const float* emb = nullptr;   // [4^k + 1][64]  emb_out; entry 4^k is the padding k-mer
+  const float4* smp = nullptr;  // [4^k + 1]      (conc, rate, sigma, 0)
+  int64_t n_kmers = 0;          // 4^k
+  int* flag = nullptr;          // device int: set by a lookup launch that met a letter outside "_ACGT"
+};
+// all k-mers in table order as int8 letter codes [n][k] (A,C,G,T = 1..4, most significant letter first; row 4^k = zeros)
+int launch_all_kmer_codes(int k, int64_t n_rows, int8_t* codes, cudaStream_t st);
+// emb_out / x_enc / x_enc16 by lookup; kidx[row] = table index (-1: not in the table, *tab.flag set)
+int launch_embed_lookup(const DevWeights& w, const KmerTables& tab, const uint8_t* bases, const int64_t* chunk_base,
+                        const int32_t* chunk_nk, const int8_t* codes, int64_t n_chunks, float* emb_out, float* x_enc,
+                        __half* x_enc16, int32_t* kidx, cudaStream_t st);
 
 // ---- k_simt.cu (fp32 CUDA-core path) --------------------------------------------------------
 enum { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_BIAS_RES_LN = 2 };
 // Y[M,N] = epi(X[M,K] @ Wt[K,N] + b); RES_LN: Y = LayerNorm(. + R) * g + beta (N must be 64)
 int launch_linear_f32(const float* X, const float* Wt, const float* b, const float* R, const float* g,
-                      const float* beta, float* Y, int64_t M, int K, int N, int epi, cudaStream_t st);
+                      const float* beta, float* Y, int64_t M, int K, int N, int epi, cudaStream_t st,
+                      const int* run_if = nullptr);
 // softmax(QK^T/sqrt(8))V per (chunk, head); qkv is [rows,192] (q|k|v), out [rows,64].
 // L = 16 (rows_per_chunk 16) or 250 (rows_per_chunk 256: pad rows are neither keys nor written... they are zeroed)
 int launch_attention_f32(const float* qkv, float* out, int64_t n_chunks, int L, int rows_per_chunk, cudaStream_t st);
@@ -57,7 +77,12 @@ int launch_attention_enc_f16out(const float* qkv, __half* out, int64_t n_chunks,
 // draws durations and rounds.  Outputs per k-mer: sigma, dur_int (+ optional conc, rate, dur_float taps).
 int launch_sampler_heads(const DevWeights& w, const float* h3, int64_t n_kmers, const s2s_run_opts& o,
                          float* sigma, int32_t* dur_int, float* conc_tap, float* rate_tap, float* dur_float_tap,
-                         cudaStream_t st);
+                         cudaStream_t st, const int* run_if = nullptr);
+// the same outputs from the per-k-mer table (rows with kidx < 0 are left to the fallback launch)
+int launch_sampler_lookup(const KmerTables& tab, const int32_t* kidx, int64_t n_kmers, const s2s_run_opts& o,
+                          float* sigma, int32_t* dur_int, float* conc_tap, float* rate_tap, float* dur_float_tap,
+                          cudaStream_t st);
+int launch_pack_smp_table(const float* conc, const float* rate, const float* sigma, int64_t n, float4* out, cudaStream_t st);
 
 // ---- k_length_regulate.cu ---------------------------------------------------------------------
 // x_dec[c, t, :] = (t < total ? enc_out[c, j(t), :] : 0) + dec_pos[t]  for t < 250, 0 for the 6 pad rows.

@@ -206,8 +206,10 @@ class _ReadPipeline:
         self.stats = dict(reads=0, chunks=0, samples=0, h2d_bytes=0, d2h_bytes=0)
         # pinned staging buffers for the int16 signal are recycled (cudaHostAlloc of ~50 MB per batch costs more than
         # the copy it serves and synchronises the device)
-        self.free_sig: "queue.Queue" = queue.Queue()
-        self.sig_cap = 0
+        # (the pool belongs to the model, so it survives the pipeline object of one predict epoch)
+        if not hasattr(model, "_sig_pool"):
+            model._sig_pool, model._sig_cap = queue.Queue(), 0
+        self.free_sig: "queue.Queue" = model._sig_pool
         self.thread = threading.Thread(target=self._writer_loop, daemon=True)
         self.thread.start()
 
@@ -217,8 +219,9 @@ class _ReadPipeline:
         except queue.Empty:
             buf = None
         if buf is None or buf.numel() < n:
-            self.sig_cap = max(self.sig_cap, int(1.25 * n) + 1)
-            buf = torch.empty(self.sig_cap, dtype=torch.int16, pin_memory=True)
+            step = 8 << 20                                   # capacities in steps of 8 Mi samples (16 MiB)
+            self.m._sig_cap = max(self.m._sig_cap, -(-int(1.25 * n) // step) * step)
+            buf = torch.empty(self.m._sig_cap, dtype=torch.int16, pin_memory=True)
         return buf
 
     def submit(self, reads, chunk_id_base=None):

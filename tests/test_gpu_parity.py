@@ -283,6 +283,36 @@ def test_shard_invariance(golden_dir):
         assert np.array_equal(x, y)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_kmer_tables_equal_direct_front_end(golden_dir, precision):
+    """emb_out / conc / rate / sigma come from per-k-mer tables built at create time.  Every stage
+    tensor and the int16 signal must be BIT-identical to the direct kernels (S2S_KMER_TABLES=0), for clean reads
+    (pure lookups) and for reads with letters outside "_ACGT" (lower case, N: the sub-batch falls back to the
+    direct kernels on the device), samplers on."""
+    from seq2squiggle_b200.engine import Engine
+    ck = torch.load(os.path.join(golden_dir, "ckpt_k9_seed1.ckpt"), map_location="cpu", weights_only=False)
+    sd, cfg = ck["state_dict"], ck["hyper_parameters"]["config"]
+    rng = np.random.default_rng(12)
+    clean = ["".join(rng.choice(list("ACGT"), n)) for n in (400, 9, 33, 1500)]
+    dirty = clean[:2] + ["ACGTNNACGTacgtACGTACGTTTGACNACGTAGCTAGCTAGCTAGGATCGAT" * 3, clean[3]]
+    opts = _opts("dna-r10-prom", precision, duration_sampling=True, noise_std=2.0, noise_sampling=True, seed=9)
+    tab = Engine(sd, cfg, device=0)
+    os.environ["S2S_KMER_TABLES"] = "0"
+    try:
+        direct = Engine(sd, cfg, device=0)
+    finally:
+        del os.environ["S2S_KMER_TABLES"]
+    names = ["emb_out", "enc_out", "sigma", "conc", "rate", "dur_float", "dur_int", "sigma_ext", "pa"]
+    for reads in (clean, dirty):
+        a, ta = tab.forward_reads(reads, opts, taps=names)
+        b, tb = direct.forward_reads(reads, opts, taps=names)
+        for n in names:
+            assert torch.equal(ta[n], tb[n]), n
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    assert sum(len(x) for x in a) > 1000
+
+
 @pytest.mark.parametrize("scale", [3.0, 4.5, 9.0])
 def test_attention_overflow_falls_back_to_exact_kernel(golden_dir, scale):
     """The pipelined attention kernel uses one reference maximum per row (max of its first 32 scores) and flags a
