@@ -259,13 +259,18 @@ def run_ours(args):
     sink.samples = 0
     barrier()
     t0 = time.perf_counter()
+    e2e_marks = [t0]
     for rd in host_reads[args.warmup:]:
         model.predict_reads(rd)
+        e2e_marks.append(time.perf_counter())
     pipe_stats = model._pipe.stats
     model.on_predict_epoch_end()
     torch.cuda.synchronize()
     barrier()
     e2e_s = time.perf_counter() - t0
+    if rank == 0:
+        sys.stderr.write("e2e per-step submit ms: " + " ".join(f"{1e3 * (b - a):.0f}" for a, b in zip(e2e_marks, e2e_marks[1:]))
+                         + f"; drain {1e3 * (t0 + e2e_s - e2e_marks[-1]):.0f} ms\n")
     e2e_samples, h2d, d2h = sink.samples, pipe_stats["h2d_bytes"], pipe_stats["d2h_bytes"]
     eng.check()
 

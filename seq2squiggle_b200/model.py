@@ -30,7 +30,8 @@ from .signal_io import BLOW5Writer
 
 logger = logging.getLogger("seq2squiggle")
 
-PIPE_CHUNKS = 65536   # chunks per pipeline piece of predict_reads (4 engine sub-batches)
+PIPE_CHUNKS = 65536   # chunks per pipeline piece of predict_reads (2 engine sub-batches)
+PIPE_DEPTH = 2        # pieces the host may queue ahead of the one whose result it waits for (absorbs host jitter)
 
 
 class _HParams(dict):
@@ -192,7 +193,7 @@ class seq2squiggle:
 
 class _ReadPipeline:
     """compute stream: H2D(bases) -> s2s_forward_reads;  copy stream: D2H(offsets) -> D2H(int16 prefix);  writer
-    thread: writer.signals = {...}; writer.save().  One batch of compute is always queued ahead of the copies."""
+    thread: writer.signals = {...}; writer.save().  PIPE_DEPTH pieces of compute are queued ahead of the copies."""
 
     def __init__(self, model: seq2squiggle):
         self.m = model
@@ -200,7 +201,7 @@ class _ReadPipeline:
         self.dev = model.device
         self.compute = torch.cuda.Stream(self.dev)
         self.copy = torch.cuda.Stream(self.dev)
-        self.pending = None          # batch whose compute is queued but whose signal has not been fetched
+        self.inflight: list = []     # pieces whose compute is queued but whose signal has not been fetched
         self.q: "queue.Queue" = queue.Queue(maxsize=4)
         self.err: Optional[BaseException] = None
         self.stats = dict(reads=0, chunks=0, samples=0, h2d_bytes=0, d2h_bytes=0)
@@ -247,9 +248,9 @@ class _ReadPipeline:
         cur = dict(names=names, raw=raw, raw_off=raw_off, off_host=off_host, off_ev=off_ev, keep=(bases, ro, co, d),
                    n_chunks=n_chunks)
         self.stats["h2d_bytes"] += bases.numel() + 8 * (ro.numel() + co.numel())
-        prev, self.pending = self.pending, cur
-        if prev is not None:
-            self._fetch(prev)
+        self.inflight.append(cur)
+        while len(self.inflight) > PIPE_DEPTH:      # the host runs PIPE_DEPTH pieces ahead of the device
+            self._fetch(self.inflight.pop(0))
 
     def _fetch(self, b):
         b["off_ev"].synchronize()
@@ -284,9 +285,8 @@ class _ReadPipeline:
                 self.err = exc
 
     def finish(self):
-        if self.pending is not None:
-            self._fetch(self.pending)
-            self.pending = None
+        while self.inflight:
+            self._fetch(self.inflight.pop(0))
         self.q.put(None)
         self.thread.join()
         self.eng.check()

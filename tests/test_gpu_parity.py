@@ -283,6 +283,24 @@ def test_shard_invariance(golden_dir):
         assert np.array_equal(x, y)
 
 
+def test_persistent_length_regulator_equals_per_chunk_kernel(golden_dir):
+    """The tensor-core path expands with k_length_regulate16 (persistent CTAs, fp16 rows, position table in registers);
+    asking for the lr_out tap routes the same call through the per-chunk kernel.  Same pA bit for bit, with sampled
+    (ragged, sometimes > 250 or tiny) durations."""
+    fx = np.load(os.path.join(golden_dir, "predict_k9_biased.npz"))
+    eng, sd, cfg = _engine(golden_dir, "ckpt_k9_seed1.ckpt", float(fx["out_bias_delta"]))
+    reads = [str(s) for s in fx["read_seqs"]]
+    for kw in (dict(duration_sampling=True, seed=3), dict(duration_sampling=False, dwell_std=6.0, dwell_mean=14.0, seed=5),
+               dict(duration_sampling=False, dwell_mean=31.0)):
+        opts = _opts("dna-r10-prom", "fp16", **kw)
+        a, ta = eng.forward_reads(reads, opts, taps=["pa", "sigma_ext", "dur_int"])
+        b, tb = eng.forward_reads(reads, opts, taps=["pa", "sigma_ext", "dur_int", "lr_out"])
+        assert torch.equal(ta["dur_int"], tb["dur_int"]) and torch.equal(ta["sigma_ext"], tb["sigma_ext"])
+        assert torch.equal(ta["pa"], tb["pa"])
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "fp16"])
 def test_kmer_tables_equal_direct_front_end(golden_dir, precision):
     """emb_out / conc / rate / sigma come from per-k-mer tables built at create time.  Every stage
