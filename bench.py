@@ -31,6 +31,10 @@ FLOP_PER_CHUNK = 85_083_392
 ATT_FLOP_PER_CHUNK_LAYER = 16_000_000       # QK^T 8.0 M + PV 8.0 M per decoder layer
 ATT_EXP_PER_CHUNK_LAYER = 8 * 250 * 250     # softmax exponentials per decoder layer
 MUFU_PER_CLK_SM = 16                        # ex2 per clock per SM (4 per SM sub-partition)
+# k_tc_attn2, one launch of 32768 chunks, `ncu --set full` (profiles/r01_attn2_ncu.txt): dram__bytes_read.sum 1.090957 GB
+# + dram__bytes_write.sum 1.043353 GB; the algorithmic traffic is 2 x 256 rows x 128 B = 65,536 B per chunk (x16 in, o16 out)
+ATT_DRAM_BYTES_PER_CHUNK_NCU = (1.090957e9 + 1.043353e9) / 32768
+ATT_ALGO_BYTES_PER_CHUNK = 2 * 256 * 128
 
 
 def synth_reads(n_reads: int, seed: int, r: int = 1000):
@@ -270,7 +274,8 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     if rank == 0:
         sys.stderr.write("e2e per-step submit ms: " + " ".join(f"{1e3 * (b - a):.0f}" for a, b in zip(e2e_marks, e2e_marks[1:]))
-                         + f"; drain {1e3 * (t0 + e2e_s - e2e_marks[-1]):.0f} ms\n")
+                         + f"; drain {1e3 * (t0 + e2e_s - e2e_marks[-1]):.0f} ms; pinned allocs in the timed region: "
+                         + f"{pipe_stats.get('pinned_allocs', 0)} ({1e3 * pipe_stats.get('pinned_alloc_s', 0.0):.0f} ms)\n")
     e2e_samples, h2d, d2h = sink.samples, pipe_stats["h2d_bytes"], pipe_stats["d2h_bytes"]
     eng.check()
 
@@ -309,12 +314,19 @@ def run_ours(args):
         sm_mhz = (clk or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
         exp_rate = ATT_EXP_PER_CHUNK_LAYER * kt["chunks_per_launch"] / (kt["ms_per_launch"] * 1e-3)
         exp_peak = MUFU_PER_CLK_SM * 148 * sm_mhz * 1e6
-        line["roofline"] = {"kernel": "k_tc_attention", "bound": "tensor", "achieved": ach, "peak": tf_peak,
-                            "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
+        line["roofline"] = {"kernel": "k_tc_attn2 (fused QKV projection + decoder attention)", "bound": "tensor",
+                            "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                            "traffic": ATT_DRAM_BYTES_PER_CHUNK_NCU * kt["chunks_per_launch"],
+                            "traffic_note": "dram__bytes_read+write per launch from the ncu --set full capture "
+                                            "(profiles/r01_attn2_ncu.txt), scaled to this run's chunks per launch; "
+                                            f"algorithmic HBM bytes per launch {ATT_ALGO_BYTES_PER_CHUNK * kt['chunks_per_launch']:.4g}",
                             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
                             "launches_timed": kt["launches"], "ms_per_launch": kt["ms_per_launch"],
                             "share_of_step": kt["share"],
-                            "note": "d_k=8 attention is bound by the softmax exponentials (MUFU.EX2), not by the tensor pipe",
+                            "note": "d_k=8 attention is bound by the softmax exponentials (XU pipe: MUFU.EX2 + F2FP), not by "
+                                    "the tensor pipe; achieved counts attention MMA FLOPs only (QK^T + PV, 16 MFLOP per "
+                                    "chunk per layer); exp.achieved counts all exponentials although a quarter of "
+                                    "them run on the FMA pipe",
                             "exp": {"achieved_gexp_s": exp_rate / 1e9, "peak_gexp_s": exp_peak / 1e9,
                                     "frac": exp_rate / exp_peak, "peak": f"16 ex2/clk/SM x 148 SMs x {sm_mhz:.0f} MHz"}}
     if args.cpu_baseline and world == 1:

@@ -589,15 +589,15 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          pk[i] = pack_half2(fmaxf(__uint_as_float(r[2 * i]) + s_b1[c * 32 + 2 * i], 0.f),
-                             fmaxf(__uint_as_float(r[2 * i + 1]) + s_b1[c * 32 + 2 * i + 1], 0.f));
+          pk[i] = pack_half2_relu(__uint_as_float(r[2 * i]) + s_b1[c * 32 + 2 * i],
+                                  __uint_as_float(r[2 * i + 1]) + s_b1[c * 32 + 2 * i + 1]);
         tmem_st_32x16(lane_addr + c * 16, pk);
         tmem_wait_ld();
         if (c + 2 < 8) tmem_ld_32x32(lane_addr + (c + 2) * 32, r);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          pk[i] = pack_half2(fmaxf(__uint_as_float(rb[2 * i]) + s_b1[(c + 1) * 32 + 2 * i], 0.f),
-                             fmaxf(__uint_as_float(rb[2 * i + 1]) + s_b1[(c + 1) * 32 + 2 * i + 1], 0.f));
+          pk[i] = pack_half2_relu(__uint_as_float(rb[2 * i]) + s_b1[(c + 1) * 32 + 2 * i],
+                                  __uint_as_float(rb[2 * i + 1]) + s_b1[(c + 1) * 32 + 2 * i + 1]);
         tmem_st_32x16(lane_addr + (c + 1) * 16, pk);
         if (c + 2 < 8) tmem_wait_ld();
       }

@@ -242,5 +242,12 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// two fp32 -> packed fp16 with ReLU fused into the conversion (one F2FP instead of two FMNMX + one F2FP)
+__device__ __forceinline__ uint32_t pack_half2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 }  // namespace tc
 }  // namespace s2s

@@ -138,13 +138,19 @@ class Engine:
     @staticmethod
     def pack_reads(reads: Sequence, k: int, pin: bool = False):
         """Host side of the boundary: concatenate read bytes, prefix offsets of bases and of chunks."""
-        bufs = [r.encode("latin-1", "replace") if isinstance(r, str) else bytes(r) for r in reads]
-        lens = np.fromiter((len(b) for b in bufs), dtype=np.int64, count=len(bufs))
-        read_off = np.zeros(len(bufs) + 1, dtype=np.int64)
+        n = len(reads)
+        if n and all(type(r) is str for r in reads):
+            # one join + one encode (latin-1 is 1 byte per character, so lengths are the string lengths)
+            lens = np.fromiter(map(len, reads), dtype=np.int64, count=n)
+            bufs = ["".join(reads).encode("latin-1", "replace")]
+        else:
+            bufs = [r.encode("latin-1", "replace") if isinstance(r, str) else bytes(r) for r in reads]
+            lens = np.fromiter((len(b) for b in bufs), dtype=np.int64, count=n)
+        read_off = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(lens, out=read_off[1:])
         nk = lens - k + 1
         nch = np.where(nk > 0, (nk + 15) // 16, 0)
-        chunk_off = np.zeros(len(bufs) + 1, dtype=np.int64)
+        chunk_off = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(nch, out=chunk_off[1:])
         bases = torch.frombuffer(bytearray(b"".join(bufs)) or bytearray(1), dtype=torch.uint8)
         ro, co = torch.from_numpy(read_off), torch.from_numpy(chunk_off)

@@ -31,7 +31,7 @@ from .signal_io import BLOW5Writer
 logger = logging.getLogger("seq2squiggle")
 
 PIPE_CHUNKS = 65536   # chunks per pipeline piece of predict_reads (2 engine sub-batches)
-PIPE_DEPTH = 2        # pieces the host may queue ahead of the one whose result it waits for (absorbs host jitter)
+PIPE_DEPTH = 3        # pieces the host may queue ahead of the one whose result it waits for (absorbs host jitter)
 
 
 class _HParams(dict):
@@ -220,9 +220,13 @@ class _ReadPipeline:
         except queue.Empty:
             buf = None
         if buf is None or buf.numel() < n:
+            import time
+            t0 = time.perf_counter()
             step = 8 << 20                                   # capacities in steps of 8 Mi samples (16 MiB)
             self.m._sig_cap = max(self.m._sig_cap, -(-int(1.25 * n) // step) * step)
             buf = torch.empty(self.m._sig_cap, dtype=torch.int16, pin_memory=True)
+            self.stats["pinned_allocs"] = self.stats.get("pinned_allocs", 0) + 1
+            self.stats["pinned_alloc_s"] = self.stats.get("pinned_alloc_s", 0.0) + time.perf_counter() - t0
         return buf
 
     def submit(self, reads, chunk_id_base=None):
