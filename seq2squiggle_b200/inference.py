@@ -9,7 +9,7 @@ and the file writer overlapped.
 Multi-GPU (``torchrun --nproc-per-node N -m seq2squiggle_b200 predict ...``): one process per GPU.  Every rank
 derives the same read list from the seed, takes a contiguous range of reads balanced by chunk count
 (``shard_reads``), keys its Philox draws by the *global* chunk index (results do not depend on N) and writes
-``<out>.part<rank>``; rank 0 stitches the parts into ``<out>`` (``merge_blow5_parts``).  No collective touches the
+``<stem>.part<rank>.blow5``; rank 0 stitches the parts into ``<out>`` (``merge_blow5_parts``).  No collective touches the
 data path; the only communication is a barrier on the control-plane process group.
 """
 from __future__ import annotations
@@ -140,6 +140,13 @@ def merge_blow5_parts(out: str, parts: Sequence[str], preserve_read_ids: bool) -
     return reads_total, samples_total
 
 
+def part_path(out: str, rank: int) -> str:
+    """Per-rank part file of a multi-GPU run: ``sim.blow5`` -> ``sim.part<rank>.blow5`` (keeps the extension, so the
+    writer factory's extension check applies to it as to any output)."""
+    stem, ext = os.path.splitext(str(out))
+    return f"{stem}.part{rank}{ext}"
+
+
 def _dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
@@ -171,7 +178,7 @@ def inference_run(config: dict, saved_weights: str, fasta: str, read_input: bool
     if world > 1:
         if not out.endswith(".blow5"):
             raise ValueError("multi-GPU predict writes BLOW5 part files: use a .blow5 output")
-        my_out = f"{out}.part{rank}"
+        my_out = part_path(out, rank)
         if rank == 0 and os.path.exists(out):
             logger.warning(f"Output file {out} already exists. File will be deleted.")
             os.remove(out)
@@ -183,6 +190,7 @@ def inference_run(config: dict, saved_weights: str, fasta: str, read_input: bool
     if saved_weights is None:
         saved_weights = get_saved_weights(profile)
 
+    local = local % max(torch.cuda.device_count(), 1)   # more ranks than GPUs (tests): ranks share devices
     torch.cuda.set_device(local)
     load_model = seq2squiggle.load_from_checkpoint(
         checkpoint_path=saved_weights, out_writer=writer, dwell_mean=dwell_mean, dwell_std=dwell_std,
@@ -221,7 +229,7 @@ def inference_run(config: dict, saved_weights: str, fasta: str, read_input: bool
             writer.save()
         dist.barrier()
         if rank == 0:
-            parts = [f"{out}.part{i}" for i in range(world)]
+            parts = [part_path(out, i) for i in range(world)]
             nr, ns = merge_blow5_parts(out, parts, preserve_read_ids)
             for p in parts:
                 os.remove(p)

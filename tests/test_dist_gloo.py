@@ -15,7 +15,7 @@ WORKER = textwrap.dedent("""
     import numpy as np
     import torch.distributed as dist
     sys.path.insert(0, %(root)r)
-    from seq2squiggle_b200.inference import chunks_of_read, merge_blow5_parts, shard_reads
+    from seq2squiggle_b200.inference import chunks_of_read, get_writer, merge_blow5_parts, part_path, shard_reads
     from seq2squiggle_b200.profiles import get_profile
     from seq2squiggle_b200.reads import sampling
     from seq2squiggle_b200.signal_io import BLOW5Writer
@@ -42,14 +42,14 @@ WORKER = textwrap.dedent("""
         sig[f"read{i}"] = fake_device(reads[i], c)
         c += counts[i]
     prof = get_profile("dna-r10-prom")
-    path = out if world == 1 else f"{out}.part{rank}"
-    w = BLOW5Writer(path, prof, True, "dna-r10-prom", False)
+    path = out if world == 1 else part_path(out, rank)
+    w, _ = get_writer(path, prof, True, 1000000, "dna-r10-prom", False)   # the same factory (and extension check) as inference_run
     w.signals = sig
     w.save()
     if world > 1:
         dist.barrier()
         if rank == 0:
-            merge_blow5_parts(out, [f"{out}.part{i}" for i in range(world)], False)
+            merge_blow5_parts(out, [part_path(out, i) for i in range(world)], False)
         dist.barrier()
         dist.destroy_process_group()
 """)

@@ -283,6 +283,57 @@ def test_shard_invariance(golden_dir):
         assert np.array_equal(x, y)
 
 
+def test_full_size_properties_of_a_bench_step(golden_dir):
+    """BASELINE configs[1] at the size bench.py times (4000 reads of the reference's expon length law, ~250 k chunks,
+    samplers on, tensor-core path), checked through size-independent properties instead of the CPU oracle:
+      * determinism: the same call twice gives the same bytes;
+      * sharding: the reads cut in three pieces with global chunk-id bases reproduce the single call bit for bit;
+      * conservation: per-read lengths == number of non-zero pA of that read's chunks, every read emits <= 250 per chunk;
+      * digitise: the int16 stream equals the stage entry point s2s_digitise applied to the surviving pA values;
+      * deterministic mode: every full chunk expands to exactly 16 x 12 = 192 positions."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import synth_reads
+    from seq2squiggle_b200.engine import Engine
+    eng, sd, cfg = _engine(golden_dir, "ckpt_k9_seed1.ckpt")
+    reads = synth_reads(4000, seed=77)
+    b, ro, co = Engine.pack_reads(reads, 9)
+    dev = [t.cuda() for t in (b, ro, co)]
+    nr, nc = ro.numel() - 1, int(co[-1])
+    assert nc > 200_000
+    opts = _opts("dna-r10-prom", "fp16", duration_sampling=True, noise_std=2.0, noise_sampling=True, seed=13)
+    raw1, off1, taps = eng.forward_reads_device(*dev, nr, nc, opts, taps=["pa"])
+    raw2, off2, _ = eng.forward_reads_device(*dev, nr, nc, opts)
+    eng.check()
+    n = int(off1[-1])
+    assert torch.equal(off1, off2) and torch.equal(raw1[:n], raw2[:n])
+    # conservation + digitise
+    pa = taps["pa"]
+    nz = (pa != 0)
+    per_chunk = nz.sum(1)
+    assert int(per_chunk.max()) <= 250 and int(nz.sum()) == n
+    cum = torch.cat([torch.zeros(1, dtype=torch.int64, device="cuda"), per_chunk.cumsum(0)])
+    assert torch.equal(off1, cum[co.cuda()])
+    prof = PROFILES["dna-r10-prom"]
+    ref = eng.digitise(pa[nz], prof["digitisation"], prof["range"], prof["offset_mean"])
+    assert torch.equal(ref, raw1[:n])
+    # sharding with global chunk-id bases
+    cuts = [0, 1300, 2900, 4000]
+    pieces = []
+    for lo, hi in zip(cuts, cuts[1:]):
+        pb, pro, pco = Engine.pack_reads(reads[lo:hi], 9)
+        r_, o_, _ = eng.forward_reads_device(pb.cuda(), pro.cuda(), pco.cuda(), hi - lo, int(pco[-1]), opts,
+                                             chunk_id_base=int(co[lo]))
+        pieces.append(r_[: int(o_[-1])])
+    eng.check()
+    assert torch.equal(torch.cat(pieces), raw1[:n])
+    # deterministic mode: 192 positions per full chunk (dwell 12.5 -> 12), zero rows after
+    det = _opts("dna-r10-prom", "fp16", dwell_mean=12.5)
+    _, _, t2 = eng.forward_reads_device(*dev, nr, nc, det, taps=["dur_int", "sigma_ext"])
+    eng.check()
+    assert bool((t2["dur_int"] == 12).all())
+
+
 def test_persistent_length_regulator_equals_per_chunk_kernel(golden_dir):
     """The tensor-core path expands with k_length_regulate16 (persistent CTAs, fp16 rows, position table in registers);
     asking for the lr_out tap routes the same call through the per-chunk kernel.  Same pA bit for bit, with sampled
