@@ -36,7 +36,7 @@ enum { kErrQkvLoad = 11, kErrQkvMma = 12, kErrAttLoad = 21, kErrAttS = 22, kErrA
 // Optional phase timing of k_tc_attn (compile with -DS2S_PHASE_TIMING): clock64() deltas of thread 0 of every CTA,
 // summed into g_phase[] and read back through s2s_debug_counters().
 __device__ unsigned long long g_phase[16];
-#ifdef S2S_PHASE_TIMING
+#if defined(S2S_PHASE_TIMING) && S2S_PHASE_TIMING == 1
 // register accumulators (constant indices): a clock read + one 64-bit add per PHASE(), nothing else
 #define PHASE_DECL long long ph_acc[16]; _Pragma("unroll") for (int i_ = 0; i_ < 16; ++i_) ph_acc[i_] = 0; long long ph_t = clock64();
 #define PHASE(i) do { long long n_ = clock64(); ph_acc[i] += n_ - ph_t; ph_t = n_; } while (0)
@@ -411,6 +411,18 @@ __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUte
   if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
+#if defined(S2S_PHASE_TIMING) && S2S_PHASE_TIMING == 2
+// FFN phase timing: thread 0 (issues the MMAs) -> g_phase[0..7], thread 32 (pure epilogue thread) -> g_phase[8..15]
+#define PHF_DECL const int phf_base = threadIdx.x == 0 ? 0 : 8; const bool phf_on = threadIdx.x == 0 || threadIdx.x == 32; \
+  long long phf_t = clock64(); long long phf_acc[8]; _Pragma("unroll") for (int i_ = 0; i_ < 8; ++i_) phf_acc[i_] = 0;
+#define PHF(i) do { if (phf_on) { long long n_ = clock64(); phf_acc[i] += n_ - phf_t; phf_t = n_; } } while (0)
+#define PHF_FLUSH do { if (phf_on) { _Pragma("unroll") for (int i_ = 0; i_ < 8; ++i_) atomicAdd(&g_phase[phf_base + i_], (unsigned long long)phf_acc[i_]); } } while (0)
+#else
+#define PHF_DECL
+#define PHF(i) do {} while (0)
+#define PHF_FLUSH do {} while (0)
+#endif
+
 #include "k_tc_attn2.cuh"
 #include "k_tc_attn4.cuh"
 
@@ -491,6 +503,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
   }
   wait_bar(&bar_w, 0, status, &s_abort, kErrFfnLoad);
   const uint32_t idesc64 = umma_idesc(128, 64, kFmtF16), idesc256 = umma_idesc(128, 256, kFmtF16);
+  PHF_DECL
   for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
     const int buf = it & 1;
     const uint32_t ph = it & 1;
@@ -502,6 +515,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
     }
     wait_bar(&bar_a[buf], (it >> 1) & 1, status, &s_abort, kErrFfnLoad);
     tcgen05_fence_after();
+    PHF(0);  // wait for the O tile (TMA)
     if (tid == 0) {  // attention output projection
       const uint32_t a0 = smem_u32(sAb), b0 = smem_u32(sWfc);
 #pragma unroll
@@ -539,8 +553,10 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
         for (int i = 0; i < 8; ++i) xr[i] = rp[i];
       }
     }
+    PHF(1);  // fc MMA issue (thread 0) + residual -> registers
     wait_bar(&bar_m0, ph, status, &s_abort, kErrFcMma);
     tcgen05_fence_after();
+    PHF(2);  // wait fc MMA
     uint32_t r[32];
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -568,6 +584,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
     }
     fence_proxy_async_smem();
     tcgen05_fence_before();
+    PHF(3);  // epilogue 1: accumulate, LayerNorm 1, fp16 Y -> shared
     __syncthreads();
     if (tid == 0) {  // hidden = Y W1^T
       tcgen05_fence_after();
@@ -579,6 +596,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
     }
     wait_bar(&bar_m1, ph, status, &s_abort, kErrFfnMma1);
     tcgen05_fence_after();
+    PHF(4);  // sync + W1 issue + wait W1 MMA
     {  // relu(D1 + b1) -> fp16, packed over the columns already consumed (loads double-buffered)
       uint32_t rb[32];
       tmem_ld_32x32(lane_addr, r);
@@ -604,6 +622,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
     }
     tmem_wait_st();
     tcgen05_fence_before();
+    PHF(5);  // epilogue 2: ReLU + pack -> TMEM
     __syncthreads();
     if (tid == 0) {  // D2 = H W2^T, A operand from TMEM
       tcgen05_fence_after();
@@ -617,6 +636,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
     for (int i = 0; i < 64; ++i) y[i] += s_v[3][i];
     wait_bar(&bar_m2, ph, status, &s_abort, kErrFfnMma2);
     tcgen05_fence_after();
+    PHF(6);  // sync + W2 issue + wait W2 MMA
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 32) {
       tmem_ld_32x32(lane_addr + 128 + c0, r);
@@ -634,7 +654,9 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
     }
     __syncthreads();  // all TMEM reads are done before the next tile's MMA overwrites the accumulators
     tcgen05_fence_after();
+    PHF(7);  // epilogue 3: accumulate, LayerNorm 2, store + closing sync
   }
+  PHF_FLUSH;
   __syncthreads();
   if (warp == 0) tmem_dealloc<256>(tmem);
 }

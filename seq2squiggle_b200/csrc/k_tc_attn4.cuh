@@ -24,7 +24,7 @@
 #pragma once
 
 constexpr int kAttn4Threads = 320;
-#ifdef S2S_PHASE_TIMING
+#if defined(S2S_PHASE_TIMING) && S2S_PHASE_TIMING == 1
 // lane 0 of softmax warp 0 and of the MMA warp add clock64() deltas to shared counters (flushed to g_phase at exit)
 #define PH4_DECL __shared__ unsigned long long s_ph[16]; if (threadIdx.x < 16) s_ph[threadIdx.x] = 0; \
   const bool ph_on = (threadIdx.x & 31) == 0 && ((threadIdx.x >> 5) == 0 || (threadIdx.x >> 5) == 8); long long ph_t = clock64();
