@@ -27,7 +27,7 @@ constexpr int kAttn2Threads = 160;
 #endif
 constexpr int kPolyExp = S2S_POLY_EXP;  // exponentials per 32 computed on the FMA pipe (fp32 polynomial) instead of MUFU
 #ifndef S2S_POLY_EXP_H2
-#define S2S_POLY_EXP_H2 4
+#define S2S_POLY_EXP_H2 5
 #endif
 constexpr int kPolyExpH2 = S2S_POLY_EXP_H2;  // pairs per 16 computed by the packed-fp16 polynomial instead of MUFU
 #ifndef S2S_POLY_BOUND_H2

@@ -496,6 +496,7 @@ int s2s_forward_chunks(s2s_handle h, const int8_t* codes_dev, int64_t n_chunks, 
                        s2s_stream stream) {
   if (!h) { set_error("null handle"); return -1; }
   if (check_opts(opts)) return -1;
+  if (n_chunks == 0) return 0;  // an empty DataLoader batch is a no-op (its tensors have no storage to point to)
   if (n_chunks < 0 || !codes_dev || !pa_out_dev) { set_error("bad arguments"); return -1; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Workspace w;

@@ -136,6 +136,25 @@ class Engine:
         return taps, out
 
     @staticmethod
+    def pack_reads_np(reads: Sequence, k: int):
+        """pack_reads without torch: (joined bytes, read offsets int64 [n+1], chunk offsets int64 [n+1])."""
+        n = len(reads)
+        if n and all(type(r) is str for r in reads):
+            lens = np.fromiter(map(len, reads), dtype=np.int64, count=n)
+            joined = "".join(reads).encode("latin-1", "replace")
+        else:
+            bufs = [r.encode("latin-1", "replace") if isinstance(r, str) else bytes(r) for r in reads]
+            lens = np.fromiter((len(b) for b in bufs), dtype=np.int64, count=n)
+            joined = b"".join(bufs)
+        read_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(lens, out=read_off[1:])
+        nk = lens - k + 1
+        nch = np.where(nk > 0, (nk + 15) // 16, 0)
+        chunk_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(nch, out=chunk_off[1:])
+        return joined, read_off, chunk_off
+
+    @staticmethod
     def pack_reads(reads: Sequence, k: int, pin: bool = False):
         """Host side of the boundary: concatenate read bytes, prefix offsets of bases and of chunks."""
         n = len(reads)

@@ -191,6 +191,34 @@ class seq2squiggle:
             self._pipe.submit(piece, base)
 
 
+class _Slot:
+    """Pinned host staging of one pipeline piece (bases + offsets in, offsets + int16 signal out).  Slots are recycled:
+    in steady state NO pinned memory is allocated — cudaHostAlloc / cudaFreeHost synchronise the whole device, and a
+    miss in torch's pinned-memory cache in the middle of a run cost the host its lead over the GPU (measured: e2e
+    runs 25 % slower at random)."""
+
+    def __init__(self):
+        self.bases = self.ro = self.co = self.off = self.sig = None
+
+    @staticmethod
+    def _grown(t, n, dtype, quantum):
+        if t is not None and t.numel() >= n:
+            return t, False
+        cap = -(-int(1.25 * n + 1) // quantum) * quantum
+        return torch.empty(cap, dtype=dtype, pin_memory=True), True
+
+    def fit_inputs(self, n_bases, n_reads):
+        self.bases, a = self._grown(self.bases, max(n_bases, 1), torch.uint8, 1 << 20)
+        self.ro, b = self._grown(self.ro, n_reads + 1, torch.int64, 1 << 12)
+        self.co, c = self._grown(self.co, n_reads + 1, torch.int64, 1 << 12)
+        self.off, d = self._grown(self.off, n_reads + 1, torch.int64, 1 << 12)
+        return a + b + c + d
+
+    def fit_signal(self, n):
+        self.sig, a = self._grown(self.sig, max(n, 1), torch.int16, 8 << 20)
+        return int(a)
+
+
 class _ReadPipeline:
     """compute stream: H2D(bases) -> s2s_forward_reads;  copy stream: D2H(offsets) -> D2H(int16 prefix);  writer
     thread: writer.signals = {...}; writer.save().  PIPE_DEPTH pieces of compute are queued ahead of the copies."""
@@ -204,54 +232,49 @@ class _ReadPipeline:
         self.inflight: list = []     # pieces whose compute is queued but whose signal has not been fetched
         self.q: "queue.Queue" = queue.Queue(maxsize=4)
         self.err: Optional[BaseException] = None
-        self.stats = dict(reads=0, chunks=0, samples=0, h2d_bytes=0, d2h_bytes=0)
-        # pinned staging buffers for the int16 signal are recycled (cudaHostAlloc of ~50 MB per batch costs more than
-        # the copy it serves and synchronises the device)
-        # (the pool belongs to the model, so it survives the pipeline object of one predict epoch)
-        if not hasattr(model, "_sig_pool"):
-            model._sig_pool, model._sig_cap = queue.Queue(), 0
-        self.free_sig: "queue.Queue" = model._sig_pool
+        self.stats = dict(reads=0, chunks=0, samples=0, h2d_bytes=0, d2h_bytes=0, pinned_allocs=0)
+        # the slot pool belongs to the model, so it survives the pipeline object of one predict epoch
+        if not hasattr(model, "_slot_pool"):
+            model._slot_pool = queue.Queue()
+        self.free_slots: "queue.Queue" = model._slot_pool
         self.thread = threading.Thread(target=self._writer_loop, daemon=True)
         self.thread.start()
 
-    def _pinned_sig(self, n: int) -> torch.Tensor:
+    def _slot(self) -> _Slot:
         try:
-            buf = self.free_sig.get_nowait()
+            return self.free_slots.get_nowait()
         except queue.Empty:
-            buf = None
-        if buf is None or buf.numel() < n:
-            import time
-            t0 = time.perf_counter()
-            step = 8 << 20                                   # capacities in steps of 8 Mi samples (16 MiB)
-            self.m._sig_cap = max(self.m._sig_cap, -(-int(1.25 * n) // step) * step)
-            buf = torch.empty(self.m._sig_cap, dtype=torch.int16, pin_memory=True)
-            self.stats["pinned_allocs"] = self.stats.get("pinned_allocs", 0) + 1
-            self.stats["pinned_alloc_s"] = self.stats.get("pinned_alloc_s", 0.0) + time.perf_counter() - t0
-        return buf
+            return _Slot()
 
     def submit(self, reads, chunk_id_base=None):
         if self.err:
             raise self.err
         m = self.m
         names = [n for _, n in reads]
-        bases, ro, co = Engine.pack_reads([s for s, _ in reads], self.eng.k, pin=True)
-        n_reads, n_chunks = len(names), int(co[-1])
+        joined, read_off, chunk_off = Engine.pack_reads_np([s for s, _ in reads], self.eng.k)
+        n_reads, n_chunks, n_bases = len(names), int(chunk_off[-1]), len(joined)
+        slot = self._slot()
+        self.stats["pinned_allocs"] += slot.fit_inputs(n_bases, n_reads)
+        slot.bases[:n_bases].numpy()[:] = np.frombuffer(joined, dtype=np.uint8)
+        slot.ro[:n_reads + 1].numpy()[:] = read_off
+        slot.co[:n_reads + 1].numpy()[:] = chunk_off
         base = m.chunks_done if chunk_id_base is None else chunk_id_base
         m.chunks_done = base + n_chunks
         with torch.cuda.stream(self.compute):
-            d = [t.to(self.dev, non_blocking=True) for t in (bases, ro, co)]
+            d = [t.to(self.dev, non_blocking=True) for t in (slot.bases[:max(n_bases, 1)], slot.ro[:n_reads + 1],
+                                                              slot.co[:n_reads + 1])]
             raw, raw_off, _ = self.eng.forward_reads_device(d[0], d[1], d[2], n_reads, n_chunks, m.run_options(), base)
             done = torch.cuda.Event()
             done.record(self.compute)
-        off_host = torch.empty(n_reads + 1, dtype=torch.int64, pin_memory=True)
+        off_host = slot.off[:n_reads + 1]
         with torch.cuda.stream(self.copy):
             self.copy.wait_event(done)
             off_host.copy_(raw_off, non_blocking=True)
             off_ev = torch.cuda.Event()
             off_ev.record(self.copy)
-        cur = dict(names=names, raw=raw, raw_off=raw_off, off_host=off_host, off_ev=off_ev, keep=(bases, ro, co, d),
+        cur = dict(names=names, raw=raw, raw_off=raw_off, off_host=off_host, off_ev=off_ev, keep=d, slot=slot,
                    n_chunks=n_chunks)
-        self.stats["h2d_bytes"] += bases.numel() + 8 * (ro.numel() + co.numel())
+        self.stats["h2d_bytes"] += n_bases + 16 * (n_reads + 1)
         self.inflight.append(cur)
         while len(self.inflight) > PIPE_DEPTH:      # the host runs PIPE_DEPTH pieces ahead of the device
             self._fetch(self.inflight.pop(0))
@@ -259,7 +282,8 @@ class _ReadPipeline:
     def _fetch(self, b):
         b["off_ev"].synchronize()
         n = int(b["off_host"][-1])
-        sig = self._pinned_sig(max(n, 1))
+        self.stats["pinned_allocs"] += b["slot"].fit_signal(n)
+        sig = b["slot"].sig
         with torch.cuda.stream(self.copy):
             sig[:n].copy_(b["raw"][:n], non_blocking=True)
             ev = torch.cuda.Event()
@@ -284,7 +308,8 @@ class _ReadPipeline:
                     w.signals = OrderedDict((name, sig[off[i]:off[i + 1]]) for i, name in enumerate(b["names"]))
                     w.save()
                     w.signals = []
-                self.free_sig.put(b.pop("sig"))
+                b.pop("sig")
+                self.free_slots.put(b.pop("slot"))
             except BaseException as exc:  # surfaced on the next submit()/finish()
                 self.err = exc
 

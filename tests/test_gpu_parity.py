@@ -283,6 +283,25 @@ def test_shard_invariance(golden_dir):
         assert np.array_equal(x, y)
 
 
+def test_empty_and_too_short_inputs(golden_dir):
+    """Edge cases of the read boundary: no reads at all, only reads shorter than k (no k-mer -> no chunk -> empty record,
+    utils.py:334-347), and such reads mixed with normal ones; plus a zero-chunk DataLoader batch."""
+    eng, sd, cfg = _engine(golden_dir, "ckpt_k9_seed1.ckpt")
+    opts = _opts("dna-r10-prom", "fp16", duration_sampling=True, noise_std=2.0, noise_sampling=True, seed=2)
+    sig, _ = eng.forward_reads([], opts)
+    assert sig == []
+    sig, _ = eng.forward_reads(["ACGT", "", "ACGTACGT"], opts)
+    assert [len(x) for x in sig] == [0, 0, 0]
+    rng = np.random.default_rng(3)
+    long_read = "".join(rng.choice(list("ACGT"), 700))
+    sig, _ = eng.forward_reads(["ACG", long_read, "", long_read[:9]], opts)
+    assert len(sig[0]) == 0 and len(sig[2]) == 0 and len(sig[1]) > 1000 and 0 < len(sig[3]) <= 250
+    alone, _ = eng.forward_reads([long_read], opts)
+    assert np.array_equal(alone[0], sig[1])          # chunk 0.. of the long read keep their global chunk ids
+    pa, _ = eng.forward_chunks(torch.zeros((0, 16, 9), dtype=torch.int8, device="cuda"), opts)
+    assert pa.shape == (0, 250)
+
+
 def test_full_size_properties_of_a_bench_step(golden_dir):
     """BASELINE configs[1] at the size bench.py times (4000 reads of the reference's expon length law, ~250 k chunks,
     samplers on, tensor-core path), checked through size-independent properties instead of the CPU oracle:
