@@ -183,12 +183,17 @@ class Engine:
         _lib.check(self.lib.s2s_check(self.handle, st), "s2s_check")
 
     def forward_reads_device(self, bases: torch.Tensor, read_off: torch.Tensor, chunk_off: torch.Tensor,
-                             n_reads: int, n_chunks: int, opts: RunOptions, chunk_id_base: int = 0, taps=None):
+                             n_reads: int, n_chunks: int, opts: RunOptions, chunk_id_base: int = 0, taps=None, out=None):
         """All inputs already on the device.  Returns (raw int16 [n_chunks*250 cap], raw_offsets int64 [n_reads+1],
-        taps dict); the valid prefix of raw is raw_offsets[-1] samples."""
+        taps dict); the valid prefix of raw is raw_offsets[-1] samples.  ``out=(raw, raw_offsets)``: caller-owned
+        output buffers (at least n_chunks*250 / n_reads+1 elements) instead of fresh allocations."""
         ws = self._workspace(n_chunks, n_reads)
-        raw = torch.empty(max(n_chunks * 250, 1), dtype=torch.int16, device=self.device)
-        raw_off = torch.empty(n_reads + 1, dtype=torch.int64, device=self.device)
+        if out is not None:
+            raw, raw_off = out
+            assert raw.dtype == torch.int16 and raw.numel() >= n_chunks * 250 and raw_off.numel() >= n_reads + 1
+        else:
+            raw = torch.empty(max(n_chunks * 250, 1), dtype=torch.int16, device=self.device)
+            raw_off = torch.empty(n_reads + 1, dtype=torch.int64, device=self.device)
         taps_c, tap_out = self._make_taps(n_chunks, taps)
         o = opts.to_c(chunk_id_base)
         st = torch.cuda.current_stream(self.device).cuda_stream

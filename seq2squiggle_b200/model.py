@@ -16,8 +16,10 @@ No Lightning: the checkpoint is a plain ``torch.load`` of the Lightning file lay
 from __future__ import annotations
 
 import logging
+import os
 import queue
 import threading
+import time
 from collections import OrderedDict
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -30,8 +32,10 @@ from .signal_io import BLOW5Writer
 
 logger = logging.getLogger("seq2squiggle")
 
+PIPE_TRACE = bool(int(os.environ.get("S2S_PIPE_TRACE", "0")))
 PIPE_CHUNKS = 65536   # chunks per pipeline piece of predict_reads (2 engine sub-batches)
 PIPE_DEPTH = 3        # pieces the host may queue ahead of the one whose result it waits for (absorbs host jitter)
+PIPE_SLOTS = PIPE_DEPTH + 6   # pinned staging slots: PIPE_DEPTH + 1 on the device side, 4 queued for the writer, 1 in save()
 
 
 class _HParams(dict):
@@ -161,8 +165,7 @@ class seq2squiggle:
 
     def on_predict_epoch_end(self):
         if self._pipe is not None:
-            self._pipe.finish()
-            self._pipe = None
+            self._pipe.finish()          # drained; streams and staging slots stay for the next epoch
         if self.results:
             self.export_and_clear_results(keep_last=False)
         logger.debug("Epoch end operation completed.")
@@ -192,36 +195,43 @@ class seq2squiggle:
 
 
 class _Slot:
-    """Pinned host staging of one pipeline piece (bases + offsets in, offsets + int16 signal out).  Slots are recycled:
-    in steady state NO pinned memory is allocated — cudaHostAlloc / cudaFreeHost synchronise the whole device, and a
-    miss in torch's pinned-memory cache in the middle of a run cost the host its lead over the GPU (measured: e2e
-    runs 25 % slower at random)."""
+    """Staging of one pipeline piece: pinned host buffers (bases + offsets in, offsets + int16 signal out) and the
+    device buffers they are copied to / from.  Slots are recycled: in steady state NOTHING is allocated, neither pinned
+    memory (cudaHostAlloc / cudaFreeHost synchronise the whole device) nor device memory (a cudaMalloc on a busy device
+    stalled the enqueueing thread for up to 0.5 s in traces) — either cost the host its lead over the GPU at random."""
 
-    def __init__(self):
-        self.bases = self.ro = self.co = self.off = self.sig = None
+    def __init__(self, device):
+        self.device = device
+        self.bases = self.ro = self.co = self.off = self.sig = None          # pinned host
+        self.bases_d = self.ro_d = self.co_d = self.raw_d = self.off_d = None  # device
 
     @staticmethod
-    def _grown(t, n, dtype, quantum):
+    def _grown(t, n, dtype, quantum, **kw):
         if t is not None and t.numel() >= n:
-            return t, False
+            return t, 0
         cap = -(-int(1.25 * n + 1) // quantum) * quantum
-        return torch.empty(cap, dtype=dtype, pin_memory=True), True
+        return torch.empty(cap, dtype=dtype, **kw), 1
 
-    def fit_inputs(self, n_bases, n_reads):
-        self.bases, a = self._grown(self.bases, max(n_bases, 1), torch.uint8, 1 << 20)
-        self.ro, b = self._grown(self.ro, n_reads + 1, torch.int64, 1 << 12)
-        self.co, c = self._grown(self.co, n_reads + 1, torch.int64, 1 << 12)
-        self.off, d = self._grown(self.off, n_reads + 1, torch.int64, 1 << 12)
-        return a + b + c + d
-
-    def fit_signal(self, n):
-        self.sig, a = self._grown(self.sig, max(n, 1), torch.int16, 8 << 20)
-        return int(a)
+    def fit(self, n_bases, n_reads, n_chunks) -> int:
+        """Make every buffer large enough for such a piece; returns the number of (re)allocations."""
+        pin, dev = dict(pin_memory=True), dict(device=self.device)
+        n_b, n_r, n_s = max(n_bases, 1), n_reads + 1, max(n_chunks * 250, 1)   # 250 samples per chunk at most
+        grew = 0
+        for name, n, dt, q, kw in (("bases", n_b, torch.uint8, 1 << 20, pin), ("ro", n_r, torch.int64, 1 << 12, pin),
+                                   ("co", n_r, torch.int64, 1 << 12, pin), ("off", n_r, torch.int64, 1 << 12, pin),
+                                   ("sig", n_s, torch.int16, 8 << 20, pin), ("bases_d", n_b, torch.uint8, 1 << 20, dev),
+                                   ("ro_d", n_r, torch.int64, 1 << 12, dev), ("co_d", n_r, torch.int64, 1 << 12, dev),
+                                   ("off_d", n_r, torch.int64, 1 << 12, dev), ("raw_d", n_s, torch.int16, 8 << 20, dev)):
+            t, g = self._grown(getattr(self, name), n, dt, q, **kw)
+            setattr(self, name, t)
+            grew += g
+        return grew
 
 
 class _ReadPipeline:
     """compute stream: H2D(bases) -> s2s_forward_reads;  copy stream: D2H(offsets) -> D2H(int16 prefix);  writer
-    thread: writer.signals = {...}; writer.save().  PIPE_DEPTH pieces of compute are queued ahead of the copies."""
+    thread: writer.signals = {...}; writer.save().  PIPE_DEPTH pieces of compute are queued ahead of the copies.
+    One pipeline (streams, staging slots) lives as long as its model; ``finish()`` drains it at the end of an epoch."""
 
     def __init__(self, model: seq2squiggle):
         self.m = model
@@ -232,39 +242,69 @@ class _ReadPipeline:
         self.inflight: list = []     # pieces whose compute is queued but whose signal has not been fetched
         self.q: "queue.Queue" = queue.Queue(maxsize=4)
         self.err: Optional[BaseException] = None
-        self.stats = dict(reads=0, chunks=0, samples=0, h2d_bytes=0, d2h_bytes=0, pinned_allocs=0)
-        # the slot pool belongs to the model, so it survives the pipeline object of one predict epoch
-        if not hasattr(model, "_slot_pool"):
-            model._slot_pool = queue.Queue()
-        self.free_slots: "queue.Queue" = model._slot_pool
-        self.thread = threading.Thread(target=self._writer_loop, daemon=True)
-        self.thread.start()
+        self.stats = dict(reads=0, chunks=0, samples=0, h2d_bytes=0, d2h_bytes=0, allocs=0)
+        self.trace: list = []        # S2S_PIPE_TRACE=1: per-piece host timestamps and device events (developer aid)
+        self.free_slots: "queue.Queue" = queue.Queue()
+        self.n_slots = 0
+        self.thread: Optional[threading.Thread] = None
 
-    def _slot(self) -> _Slot:
-        try:
-            return self.free_slots.get_nowait()
-        except queue.Empty:
-            return _Slot()
+    def _ensure_writer(self):
+        if self.thread is None or not self.thread.is_alive():
+            self.thread = threading.Thread(target=self._writer_loop, daemon=True)
+            self.thread.start()
+
+    def _slot(self, n_bases, n_reads, n_chunks) -> _Slot:
+        """A free staging slot fitted to the piece.  The whole pool of PIPE_SLOTS slots (in flight on the device +
+        queued for the writer + being written) is created on the first piece, sized for pieces like it; afterwards the
+        host waits for the writer thread to hand a slot back instead of allocating."""
+        if self.n_slots == 0:
+            with torch.cuda.stream(self.compute):
+                for _ in range(PIPE_SLOTS):
+                    sl = _Slot(self.dev)
+                    sl.fit(n_bases, n_reads, n_chunks)
+                    self.free_slots.put(sl)
+            self.n_slots = PIPE_SLOTS
+        while True:
+            if self.err:
+                raise self.err
+            try:
+                sl = self.free_slots.get(timeout=0.5)
+                break
+            except queue.Empty:
+                continue
+        with torch.cuda.stream(self.compute):
+            self.stats["allocs"] += sl.fit(n_bases, n_reads, n_chunks)
+        return sl
 
     def submit(self, reads, chunk_id_base=None):
         if self.err:
             raise self.err
+        self._ensure_writer()
         m = self.m
+        t_sub = time.perf_counter()
         names = [n for _, n in reads]
         joined, read_off, chunk_off = Engine.pack_reads_np([s for s, _ in reads], self.eng.k)
         n_reads, n_chunks, n_bases = len(names), int(chunk_off[-1]), len(joined)
-        slot = self._slot()
-        self.stats["pinned_allocs"] += slot.fit_inputs(n_bases, n_reads)
+        slot = self._slot(n_bases, n_reads, n_chunks)
         slot.bases[:n_bases].numpy()[:] = np.frombuffer(joined, dtype=np.uint8)
         slot.ro[:n_reads + 1].numpy()[:] = read_off
         slot.co[:n_reads + 1].numpy()[:] = chunk_off
         base = m.chunks_done if chunk_id_base is None else chunk_id_base
         m.chunks_done = base + n_chunks
+        t_packed = time.perf_counter()
+        nb = max(n_bases, 1)
         with torch.cuda.stream(self.compute):
-            d = [t.to(self.dev, non_blocking=True) for t in (slot.bases[:max(n_bases, 1)], slot.ro[:n_reads + 1],
-                                                              slot.co[:n_reads + 1])]
-            raw, raw_off, _ = self.eng.forward_reads_device(d[0], d[1], d[2], n_reads, n_chunks, m.run_options(), base)
-            done = torch.cuda.Event()
+            ev_start = None
+            if PIPE_TRACE:
+                ev_start = torch.cuda.Event(enable_timing=True)
+                ev_start.record(self.compute)
+            slot.bases_d[:nb].copy_(slot.bases[:nb], non_blocking=True)
+            slot.ro_d[:n_reads + 1].copy_(slot.ro[:n_reads + 1], non_blocking=True)
+            slot.co_d[:n_reads + 1].copy_(slot.co[:n_reads + 1], non_blocking=True)
+            raw, raw_off, _ = self.eng.forward_reads_device(slot.bases_d[:nb], slot.ro_d[:n_reads + 1],
+                                                            slot.co_d[:n_reads + 1], n_reads, n_chunks, m.run_options(),
+                                                            base, out=(slot.raw_d, slot.off_d[:n_reads + 1]))
+            done = torch.cuda.Event(enable_timing=PIPE_TRACE)
             done.record(self.compute)
         off_host = slot.off[:n_reads + 1]
         with torch.cuda.stream(self.copy):
@@ -272,23 +312,28 @@ class _ReadPipeline:
             off_host.copy_(raw_off, non_blocking=True)
             off_ev = torch.cuda.Event()
             off_ev.record(self.copy)
-        cur = dict(names=names, raw=raw, raw_off=raw_off, off_host=off_host, off_ev=off_ev, keep=d, slot=slot,
-                   n_chunks=n_chunks)
+        cur = dict(names=names, off_host=off_host, off_ev=off_ev, slot=slot, n_chunks=n_chunks)
+        if PIPE_TRACE:
+            cur["trace"] = dict(t_sub=t_sub, t_packed=t_packed, t_enq=time.perf_counter(), ev_start=ev_start, ev_done=done)
         self.stats["h2d_bytes"] += n_bases + 16 * (n_reads + 1)
         self.inflight.append(cur)
         while len(self.inflight) > PIPE_DEPTH:      # the host runs PIPE_DEPTH pieces ahead of the device
             self._fetch(self.inflight.pop(0))
 
     def _fetch(self, b):
+        t_f0 = time.perf_counter()
         b["off_ev"].synchronize()
+        if PIPE_TRACE:
+            tr = b["trace"]
+            tr.update(t_fetch0=t_f0, t_fetch1=time.perf_counter())
+            self.trace.append(tr)
         n = int(b["off_host"][-1])
-        self.stats["pinned_allocs"] += b["slot"].fit_signal(n)
-        sig = b["slot"].sig
+        slot = b["slot"]
         with torch.cuda.stream(self.copy):
-            sig[:n].copy_(b["raw"][:n], non_blocking=True)
+            slot.sig[:n].copy_(slot.raw_d[:n], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.copy)
-        b.update(sig=sig, n=n, sig_ev=ev)
+        b.update(n=n, sig_ev=ev)
         self.stats["d2h_bytes"] += 2 * n + 8 * b["off_host"].numel()
         self.stats["reads"] += len(b["names"]); self.stats["chunks"] += b["n_chunks"]; self.stats["samples"] += n
         self.q.put(b)
@@ -300,24 +345,26 @@ class _ReadPipeline:
                 return
             try:
                 b["sig_ev"].synchronize()
-                b["raw"] = b["raw_off"] = b["keep"] = None            # device buffers back to the allocator
                 off = b["off_host"].numpy()
-                sig = b["sig"].numpy()
+                sig = b["slot"].sig.numpy()
                 w = self.m.out_writer
                 if w is not None:      # the views are valid until save() returns (writer plug-point contract)
                     w.signals = OrderedDict((name, sig[off[i]:off[i + 1]]) for i, name in enumerate(b["names"]))
                     w.save()
                     w.signals = []
-                b.pop("sig")
-                self.free_slots.put(b.pop("slot"))
             except BaseException as exc:  # surfaced on the next submit()/finish()
                 self.err = exc
+            finally:
+                self.free_slots.put(b.pop("slot"))
 
     def finish(self):
+        """Drain: fetch everything in flight, let the writer finish, surface errors.  The pipeline stays usable."""
         while self.inflight:
             self._fetch(self.inflight.pop(0))
-        self.q.put(None)
-        self.thread.join()
+        if self.thread is not None and self.thread.is_alive():
+            self.q.put(None)
+            self.thread.join()
         self.eng.check()
         if self.err:
-            raise self.err
+            err, self.err = self.err, None
+            raise err

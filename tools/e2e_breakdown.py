@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Developer tool: where the end-to-end (host reads -> host int16) time of model.predict_reads goes.
-  gpurun -- python tools/e2e_breakdown.py"""
+"""Developer tool: where the end-to-end (host reads -> host int16) time of model.predict_reads goes.  Warm-up of W full
+steps, then REPS repetitions of STEPS steps, each on a fresh pipeline (like bench.py); with S2S_PIPE_TRACE=1 the slowest
+repetition's per-piece trace (host timestamps + device events) is printed.
+  S2S_PIPE_TRACE=1 gpurun -- python tools/e2e_breakdown.py"""
 import os
 import sys
 import time
@@ -11,30 +13,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import synth_reads  # noqa: E402
 from seq2squiggle_b200 import model as M  # noqa: E402
 from seq2squiggle_b200.checkpoint import random_init_checkpoint, set_config  # noqa: E402
-from seq2squiggle_b200.engine import Engine  # noqa: E402
 from seq2squiggle_b200.profiles import get_profile  # noqa: E402
 
 
 class Sink:
     profile, profile_name = get_profile("dna-r10-prom"), "dna-r10-prom"
-    signals, samples, t = None, 0, 0.0
+    signals, samples = None, 0
 
     def save(self):
-        t0 = time.perf_counter()
         self.samples += sum(len(v) for v in self.signals.values())
-        self.t += time.perf_counter() - t0
-
-
-T = {}
-
-
-def timed(name, fn):
-    def w(*a, **k):
-        t0 = time.perf_counter()
-        r = fn(*a, **k)
-        T[name] = T.get(name, 0.0) + time.perf_counter() - t0
-        return r
-    return w
 
 
 cfg = set_config(None)
@@ -42,28 +29,39 @@ sd = random_init_checkpoint(cfg, 1)["state_dict"]
 sink = Sink()
 m = M.seq2squiggle(config=cfg, state_dict=sd, out_writer=sink, dwell_mean=12.5, dwell_std=0.0, noise_std=2.0,
                    noise_sampling=True, duration_sampling=True, min_noise=0.0, min_duration=3, device=0, seed=7)
-steps = int(os.environ.get("STEPS", 8))
-host_reads = [[(r.decode("latin-1"), str(j)) for j, r in enumerate(synth_reads(4000, seed=i))] for i in range(steps)]
-m.predict_reads(host_reads[0][:64])
-m.on_predict_epoch_end()
-Engine.pack_reads = staticmethod(timed("pack_reads", Engine.pack_reads))
-M._ReadPipeline._fetch = timed("fetch(prev): wait offsets + queue D2H", M._ReadPipeline._fetch)
-M._ReadPipeline.submit = timed("submit total", M._ReadPipeline.submit)
-m.engine.forward_reads_device = timed("forward_reads_device (enqueue)", m.engine.forward_reads_device)
-sink.samples = 0
-torch.cuda.synchronize()
-t0 = time.perf_counter()
-per = []
-for rd in host_reads:
-    ta = time.perf_counter()
+steps, reps, warm = int(os.environ.get("STEPS", 5)), int(os.environ.get("REPS", 6)), int(os.environ.get("WARMUP", 3))
+host_reads = [[(r.decode("latin-1"), str(j)) for j, r in enumerate(synth_reads(4000, seed=i))] for i in range(steps + warm)]
+for rd in host_reads[:warm]:
     m.predict_reads(rd)
-    per.append(1e3 * (time.perf_counter() - ta))
-print("per-step submit ms:", " ".join(f"{x:.0f}" for x in per))
-t1 = time.perf_counter()
 m.on_predict_epoch_end()
-torch.cuda.synchronize()
-t2 = time.perf_counter()
-print(f"{steps} steps: submit loop {1e3 * (t1 - t0):.1f} ms, drain {1e3 * (t2 - t1):.1f} ms, total/step {1e3 * (t2 - t0) / steps:.1f} ms, "
-      f"{sink.samples / (t2 - t0) / 1e6:.1f} M samples/s; sink.save {1e3 * sink.t:.1f} ms")
-for k, v in T.items():
-    print(f"  {k:42s} {1e3 * v / steps:8.2f} ms/step")
+worst = None
+for rep in range(reps):
+    sink.samples = 0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    per = []
+    for rd in host_reads[warm:]:
+        ta = time.perf_counter()
+        m.predict_reads(rd)
+        per.append(1e3 * (time.perf_counter() - ta))
+    pipe = m._pipe
+    t1 = time.perf_counter()
+    m.on_predict_epoch_end()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"rep {rep}: per-step submit ms {' '.join(f'{x:.0f}' for x in per)}; drain {1e3 * (t2 - t1):.0f} ms; "
+          f"{sink.samples / (t2 - t0) / 1e6:.1f} M samples/s; staging allocs {pipe.stats['allocs']}")
+    if pipe.trace and (worst is None or t2 - t0 > worst[0]):
+        worst = (t2 - t0, rep, t0, list(pipe.trace))
+    pipe.trace.clear()
+if worst:
+    _, rep, t0, tr = worst
+    e0 = tr[0]["ev_start"]
+    print(f"slowest repetition: {rep}")
+    print("piece:  host submit@ms  pack ms  enqueue ms | fetch wait ms | device start@ms  device ms  idle-before ms")
+    prev_end = 0.0
+    for i, x in enumerate(tr):
+        ds, de = e0.elapsed_time(x["ev_start"]), e0.elapsed_time(x["ev_done"])
+        print(f"{i:3d}  {1e3 * (x['t_sub'] - t0):9.1f} {1e3 * (x['t_packed'] - x['t_sub']):8.1f} {1e3 * (x['t_enq'] - x['t_packed']):8.1f} | "
+              f"{1e3 * (x['t_fetch1'] - x['t_fetch0']):8.1f} | {ds:9.1f} {de - ds:8.1f} {ds - prev_end:8.1f}")
+        prev_end = de
