@@ -179,13 +179,28 @@ __global__ void __launch_bounds__(256) k_attention_dec_f32(const float* __restri
 }
 
 // Encoder length (16 keys): one CTA of 128 threads per chunk, thread = (head, query).
-template <typename OutT>
-__global__ void __launch_bounds__(128) k_attention_enc_f32(const float* __restrict__ qkv, OutT* __restrict__ out) {
+template <typename OutT, typename InT = float>
+__global__ void __launch_bounds__(128) k_attention_enc_f32(const InT* __restrict__ qkv, OutT* __restrict__ out) {
   __shared__ __align__(16) float s[S2S_L_ENC][192];
   const int64_t c = blockIdx.x;
   const int tid = threadIdx.x;
-  const float4* src = reinterpret_cast<const float4*>(qkv + c * S2S_L_ENC * 192);
-  for (int i = tid; i < S2S_L_ENC * 192 / 4; i += 128) reinterpret_cast<float4*>(&s[0][0])[i] = src[i];
+  if constexpr (sizeof(InT) == 4) {
+    const float4* src = reinterpret_cast<const float4*>(qkv + c * S2S_L_ENC * 192);
+    for (int i = tid; i < S2S_L_ENC * 192 / 4; i += 128) reinterpret_cast<float4*>(&s[0][0])[i] = src[i];
+  } else {  // fp16 q|k|v from the tensor-core projection: 16-byte loads of 8 values, widened into the fp32 tile
+    const uint4* src = reinterpret_cast<const uint4*>(qkv + c * S2S_L_ENC * 192);
+    for (int i = tid; i < S2S_L_ENC * 192 / 8; i += 128) {
+      const uint4 v = src[i];
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+      float* dst = &s[0][0] + 8 * i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[j]));
+        dst[2 * j] = f.x;
+        dst[2 * j + 1] = f.y;
+      }
+    }
+  }
   __syncthreads();
   const int h = tid >> 4, qi = tid & 15;
   const float scale = 0.35355339059327373f;
@@ -236,9 +251,9 @@ int launch_attention_f32(const float* qkv, float* out, int64_t n_chunks, int L, 
   return 0;
 }
 
-int launch_attention_enc_f16out(const float* qkv, __half* out, int64_t n_chunks, cudaStream_t st) {
+int launch_attention_enc_f16(const __half* qkv, __half* out, int64_t n_chunks, cudaStream_t st) {
   if (n_chunks == 0) return 0;
-  k_attention_enc_f32<__half><<<(unsigned)n_chunks, 128, 0, st>>>(qkv, out);
+  k_attention_enc_f32<__half, __half><<<(unsigned)n_chunks, 128, 0, st>>>(qkv, out);
   S2S_LAUNCH_CHECK();
   return 0;
 }

@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
 // =================================================================================================
 __global__ void __launch_bounds__(128, 2) k_tc_qkv_plain(const __grid_constant__ CUtensorMap tmX,
                                                          const __grid_constant__ CUtensorMap tmW,
-                                                         const float* __restrict__ bias, float* __restrict__ qkv,
+                                                         const float* __restrict__ bias, __half* __restrict__ qkv,
                                                          int64_t n_rows, int* status) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_w, bar_a[2], bar_mma;
@@ -731,11 +731,13 @@ __global__ void __launch_bounds__(128, 2) k_tc_qkv_plain(const __grid_constant__
       tmem_ld_32x32(lane_addr + c0, r);
       tmem_wait_ld();
       if (row < n_rows) {
-        float4* dst = reinterpret_cast<float4*>(qkv + row * 192 + c0);
+        uint4* dst = reinterpret_cast<uint4*>(qkv + row * 192 + c0);   // fp16 q|k|v: 384 B per row instead of 768
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          dst[i] = make_float4(__uint_as_float(r[4 * i]) + s_bias[c0 + 4 * i], __uint_as_float(r[4 * i + 1]) + s_bias[c0 + 4 * i + 1],
-                               __uint_as_float(r[4 * i + 2]) + s_bias[c0 + 4 * i + 2], __uint_as_float(r[4 * i + 3]) + s_bias[c0 + 4 * i + 3]);
+        for (int i = 0; i < 4; ++i)
+          dst[i] = make_uint4(pack_half2(__uint_as_float(r[8 * i]) + s_bias[c0 + 8 * i], __uint_as_float(r[8 * i + 1]) + s_bias[c0 + 8 * i + 1]),
+                              pack_half2(__uint_as_float(r[8 * i + 2]) + s_bias[c0 + 8 * i + 2], __uint_as_float(r[8 * i + 3]) + s_bias[c0 + 8 * i + 3]),
+                              pack_half2(__uint_as_float(r[8 * i + 4]) + s_bias[c0 + 8 * i + 4], __uint_as_float(r[8 * i + 5]) + s_bias[c0 + 8 * i + 5]),
+                              pack_half2(__uint_as_float(r[8 * i + 6]) + s_bias[c0 + 8 * i + 6], __uint_as_float(r[8 * i + 7]) + s_bias[c0 + 8 * i + 7]));
       }
     }
     tcgen05_fence_before();
@@ -917,9 +919,10 @@ int tc_encoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, 
       set_error("cuTensorMapEncodeTiled failed for a weight tensor");
       return -1;
     }
-    k_tc_qkv_plain<<<grid2, 128, kSmemQkv, st>>>(tmX, tmWqkv, bl.bqkv, qkv32, (int64_t)rows, s.d_status);
+    __half* qkv16 = reinterpret_cast<__half*>(qkv32);   // the fp32 scratch of the SIMT path, used as fp16 here
+    k_tc_qkv_plain<<<grid2, 128, kSmemQkv, st>>>(tmX, tmWqkv, bl.bqkv, qkv16, (int64_t)rows, s.d_status);
     S2S_LAUNCH_CHECK();
-    if (launch_attention_enc_f16out(qkv32, o16, n_chunks, st)) return -1;
+    if (launch_attention_enc_f16(qkv16, o16, n_chunks, st)) return -1;
     k_tc_fc_ffn<true, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, bl.fc_b, bl.ln1_w, bl.ln1_b, bl.b1, bl.b2,
                                                            bl.ln2_w, bl.ln2_b, x32, x16, nullptr, nullptr, nullptr, n_tiles,
                                                            s.d_status);
