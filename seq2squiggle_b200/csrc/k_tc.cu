@@ -198,10 +198,14 @@ __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUte
                                                     const __grid_constant__ CUtensorMap tmWg,
                                                     const float* __restrict__ bias_g, __half* __restrict__ o16,
                                                     int n_units, const int* __restrict__ unit_flags,
-                                                    const int* __restrict__ n_flagged, int* status) {
+                                                    const int* __restrict__ n_flagged, int* status,
+                                                    int* __restrict__ hint_out = nullptr) {
   // As the exact fallback of k_tc_attn2 (unit_flags != nullptr) only the flagged units are recomputed.
   if (unit_flags) {
     const int nf = *n_flagged;
+    // n_flagged counts flagging WARPS (up to 4 per unit).  More than half of them: this layer's attention is too sharp
+    // for the single-reference kernel; the hint makes the next sub-batches skip it (see k_tc_attn2).
+    if (hint_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *hint_out = nf > 2 * n_units ? 1 : 0;
     if (nf == 0) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_phase[12], (unsigned long long)nf);
   }
@@ -424,6 +428,21 @@ __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUte
 #endif
 
 #include "k_tc_attn2.cuh"
+
+// Adaptive fallback gate, launched in front of k_tc_attn2.  When the previous sub-batch of this layer sent most of its
+// units to the exact kernel (hint set by k_tc_attn), running the single-reference kernel first only wastes its time
+// (measured with W_q, W_k scaled x4: 1.21 M chunks/s with both kernels, 1.95 M with the exact kernel alone): every
+// unit is flagged here and status[1] tells k_tc_attn2 to return at once.  The host re-probes every 16th call.
+__global__ void k_attn_gate(const int* __restrict__ hint, int probe, int n_units, int* __restrict__ unit_flags,
+                            int* __restrict__ n_flagged, int* __restrict__ status) {
+  const bool skip = !probe && *hint != 0;
+  if (skip)
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) unit_flags[u] = 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    status[1] = skip ? 1 : 0;
+    if (skip) *n_flagged = 4 * n_units;
+  }
+}
 #include "k_tc_attn4.cuh"
 
 // =================================================================================================
@@ -826,6 +845,7 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* p_out
   const int n_units = (int)(2 * n_chunks);
   int32_t* d_flags = b.flags;  // [0] = number of flagged units, [1..] = per-unit overflow flags (workspace)
   const int grid_att = n_units < 2 * s.sm_count ? n_units : 2 * s.sm_count;  // even stride: a CTA keeps its head group
+  ++s.attn_calls;
   for (int l = 0; l < w.cfg.decoder_layers; ++l) {
     const BlockDev& bl = w.dec[l];
     CUtensorMap tmWg, tmWfc, tmW1, tmW2;
@@ -858,6 +878,10 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* p_out
       // and no row-max pass, but measured no faster (4.76 vs 4.76-4.92 ms per 32768 chunks): the exp pass is bound by the
       // XU pipe, which also executes the F2FP packs (8 (1 - f) + 1 clk per exponential per scheduler).
       static const int attn_bound = getenv("S2S_ATTN_BOUND") ? atoi(getenv("S2S_ATTN_BOUND")) : 0;
+      // per-layer hint words live behind the status word; every 16th call probes the fast kernel again
+      int* hint = s.d_status + 8 + l;
+      if (attn_ver != 4)
+        k_attn_gate<<<64, 256, 0, st>>>(hint, s.attn_calls % 16 == 15, n_units, d_flags + 1, d_flags, s.d_status);
       if (attn_ver != 4 && attn_bound)
         k_tc_attn2<true><<<grid2a, kAttn2Threads, smem2a, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags,
                                                                    s.d_status);
@@ -868,7 +892,8 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* p_out
         k_tc_attn4<<<grid_att, kAttn4Threads, kSmemAtt, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags,
                                                               s.d_status);
       S2S_LAUNCH_CHECK();
-      k_tc_attn<<<grid_att, 128, kSmemAtt, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags, s.d_status);
+      k_tc_attn<<<grid_att, 128, kSmemAtt, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags, s.d_status,
+                                                 attn_ver != 4 ? hint : nullptr);
     }
     S2S_LAUNCH_CHECK();
     if (s.prof_on) {

@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(kAttn2Threads, 2) k_tc_attn2(const __grid_cons
   uint8_t* sV = smem + 4 * kSlab;      // 4 key quarters x [64 rows (4 heads x 16) x 128 B]
   uint8_t* sW = smem + 6 * kSlab;      // [96 x 128 B] weight block of the CTA's head group
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) s_go = (*status == 0);
+  // status[0]: a barrier wait timed out somewhere; status[1]: k_attn_gate sent this launch's units to the exact kernel
+  if (tid == 0) s_go = (status[0] == 0 && status[1] == 0);
   __syncthreads();
   if (!s_go) return;
   if (warp == 0) tmem_alloc<256>(&s_tmem);

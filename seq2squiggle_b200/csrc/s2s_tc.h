@@ -16,6 +16,7 @@ struct TcState {
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_events;   // start/stop pairs
   int64_t prof_chunks = 0;
+  int64_t attn_calls = 0;        // decoder calls so far: every 16th ignores the "attention too sharp" hints (re-probe)
 };
 
 // Per-sub-batch device buffers of the tensor-core path (carved from the caller's workspace).
