@@ -152,6 +152,21 @@ def test_batching_and_sharding():
     assert shard_reads([5], 2) in ([(0, 0), (0, 1)], [(0, 1), (1, 1)])
 
 
+def test_pack_reads_variants_agree():
+    """Engine.pack_reads (torch tensors) and Engine.pack_reads_np (bytes + numpy, used by the staging pipeline) build the
+    same byte stream and offsets for str, bytes and mixed inputs, including reads shorter than k and empty input."""
+    from seq2squiggle_b200.engine import Engine
+    reads = ["ACGTACGTACGTACGTACGTACGTA", "ACG", "", "N" * 40, "acgtacgtacgt" * 9]
+    for inp in (reads, [r.encode() for r in reads], [reads[0], reads[1].encode(), reads[2], reads[3].encode(), reads[4]]):
+        bases, ro, co = Engine.pack_reads(inp, 9)
+        joined, ro2, co2 = Engine.pack_reads_np(inp, 9)
+        assert bytes(bases.numpy().tobytes())[:len(joined)] == joined
+        assert ro.tolist() == ro2.tolist() == [0, 25, 28, 28, 68, 176]
+        assert co.tolist() == co2.tolist() == [0, 2, 2, 2, 4, 11]
+    joined, ro2, co2 = Engine.pack_reads_np([], 9)
+    assert joined == b"" and ro2.tolist() == [0] and co2.tolist() == [0]
+
+
 def test_merge_blow5_parts_equals_single_writer(tmp_path):
     from seq2squiggle_b200.inference import merge_blow5_parts
     from seq2squiggle_b200.profiles import get_profile
