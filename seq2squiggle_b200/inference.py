@@ -199,7 +199,10 @@ def inference_run(config: dict, saved_weights: str, fasta: str, read_input: bool
         precision=precision)
     check_model(load_model.hparams.config, config)
 
-    reads, total_l = get_reads(fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len)
+    # single process: reads are sampled lazily, batch by batch, while the GPU works on the previous batches (the
+    # sampler is sequential Python); the sharded multi-process run needs the whole list to balance the ranks
+    reads, total_l = get_reads(fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len,
+                               stream=(world == 1), cheap_names=not preserve_read_ids)
     k = config["seq_kmer"]
     chunk_base = 0
     if world > 1:

@@ -218,9 +218,16 @@ def reverse_complement(f: str) -> str:
 def sampling(num_seqs, genome_seqs, genome_lens, r, seed, total_len, distr, profile, min_read_len=30,
              max_retries=20) -> List[str]:
     """utils.py:415-479: sample ``num_seqs`` reads from the genome(s)."""
+    return list(sampling_iter(num_seqs, genome_seqs, genome_lens, r, seed, total_len, distr, profile, min_read_len,
+                              max_retries))
+
+
+def sampling_iter(num_seqs, genome_seqs, genome_lens, r, seed, total_len, distr, profile, min_read_len=30,
+                  max_retries=20) -> Generator[str, None, None]:
+    """``sampling`` as a generator: the same reads in the same order (the same calls on the ``random`` module and the
+    same per-read seeds), produced on demand so that the caller can overlap sampling with the GPU."""
     draw = DISTR_FUNCS[distr]
     total_genome_len = sum(genome_lens)
-    sampled = []
     dna = profile.startswith("dna")
     # first-attempt lengths of all reads in one vectorised pass (default law, 32-bit seeds); retries and the other
     # laws take the per-seed path.  Identical values either way.
@@ -246,14 +253,13 @@ def sampling(num_seqs, genome_seqs, genome_lens, r, seed, total_len, distr, prof
                     read = N_to_ACTG(read)
                 if read_strand == "-":
                     read = reverse_complement(read)
-                sampled.append(read)
+                yield read
                 break
             retries += 1
             if retries >= max_retries:
                 logger.debug(f"Failed to sample a valid read after {max_retries} retries for read {read_i}. Skipping this read.")
             else:
                 logger.debug(f"Retrying to sample read {read_i} (attempt {retries + 1}/{max_retries})")
-    return sampled
 
 
 def export_fasta(read_l: Iterable[str], fasta) -> str:
@@ -266,14 +272,18 @@ def export_fasta(read_l: Iterable[str], fasta) -> str:
     return out_file
 
 
-def yield_reads(reads: Iterable[str]):
-    """utils.py:489-490."""
+def yield_reads(reads: Iterable[str], cheap_names: bool = False):
+    """utils.py:489-490: ``(read, uuid4 name)``.  ``cheap_names``: the names are only dictionary keys (the writers
+    replace them with indexed ids unless ``--preserve-read-ids``), so a counter does instead of 100k ``uuid4()`` calls."""
+    if cheap_names:
+        return ((read, f"read_{i}") for i, read in enumerate(reads))
     return ((read, str(uuid4())) for read in reads)
 
 
 def sample_reads_from_reference(genome_seqs, genome_lens, n, r, c, config, fasta, seed, save=False, distr="expon",
-                                profile="dna-r10-min", min_read_len=30):
-    """utils.py:493-582: argument validation (same messages) + sampling."""
+                                profile="dna-r10-min", min_read_len=30, stream=False, cheap_names=False):
+    """utils.py:493-582: argument validation (same messages) + sampling.  ``stream``: return a lazy generator (and no
+    length hint) instead of sampling every read up front."""
     logger.debug("Generating reads from the reference input file.")
     if n <= 0 and c <= 0:
         logger.error("You need to specify the coverage c or the number of reads n")
@@ -293,15 +303,20 @@ def sample_reads_from_reference(genome_seqs, genome_lens, n, r, c, config, fasta
             f"Average reference sequence length ({avg_genome_len:.2f}) is smaller than the desired average read length ({r})."
             " If the sampled read length is higher than the reference sequence length, they will be skipped."
             " Consider reducing the desired average read length via -r.")
+    if stream and not save:
+        return yield_reads(sampling_iter(seq_num, genome_seqs, genome_lens, r, seed, total_len, distr, profile,
+                                         min_read_len), cheap_names), None
     read_list = sampling(seq_num, genome_seqs, genome_lens, r, seed, total_len, distr, profile, min_read_len)
     total_l = sum(round(len(read) / config["max_dna_len"]) for read in read_list)
-    reads_fasta = export_fasta(read_list, fasta) if save else yield_reads(read_list)
+    reads_fasta = export_fasta(read_list, fasta) if save else yield_reads(read_list, cheap_names)
     logger.debug("Generating reads finished.")
     return reads_fasta, total_l
 
 
-def get_reads(fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len, save=False):
-    """utils.py:641-671: ``(generator of (sequence, name), length hint)``."""
+def get_reads(fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len, save=False, stream=False,
+              cheap_names=False):
+    """utils.py:641-671: ``(generator of (sequence, name), length hint)``.  ``stream`` / ``cheap_names`` (reference mode
+    only): sample lazily (length hint None) / name the reads with a counter instead of ``uuid4()``."""
     logger.info(f"{'Read' if read_input else 'Reference'} mode.")
     is_rna = profile.startswith("rna")
     if read_input:
@@ -318,5 +333,5 @@ def get_reads(fasta, read_input, n, r, c, config, distr, seed, profile, min_read
         return generator(), sum(round(len(seq) / config["max_dna_len"]) for seq, _ in sampled)
     genome_seqs, genome_lens = preprocess_genome(fasta)
     reads_fasta, total_l = sample_reads_from_reference(genome_seqs, genome_lens, n, r, c, config, fasta, seed, save,
-                                                       distr, profile, min_read_len)
+                                                       distr, profile, min_read_len, stream, cheap_names)
     return read_fasta(reads_fasta, is_rna) if save else (reads_fasta, total_l)

@@ -66,6 +66,30 @@ def test_sampling_fast_path_equals_slow_path():
     assert fast == slow_same_seed and len(fast) > 250
 
 
+def test_streamed_sampling_equals_eager(tmp_path):
+    """get_reads(stream=True) (what the single-process inference_run uses to overlap sampling with the GPU) yields the
+    same reads in the same order as the eager list; cheap names are unique."""
+    import random
+    from seq2squiggle_b200 import reads as R
+    rng = np.random.default_rng(8)
+    g = "".join(rng.choice(list("ACGTN"), 30000, p=[0.245, 0.245, 0.245, 0.245, 0.02]))
+    fasta = tmp_path / "g.fasta"
+    fasta.write_text(">chr1\n" + "\n".join(g[i:i + 70] for i in range(0, len(g), 70)) + "\n")
+    cfg = {"max_dna_len": 16}
+    random.seed(4)
+    eager, hint = R.get_reads(str(fasta), False, 400, 600, -1, cfg, "expon", 4, "dna-r10-prom", 30)
+    eager = [s for s, _ in eager]
+    random.seed(4)
+    lazy, hint2 = R.get_reads(str(fasta), False, 400, 600, -1, cfg, "expon", 4, "dna-r10-prom", 30, stream=True,
+                              cheap_names=True)
+    lazy = list(lazy)
+    assert hint > 0 and hint2 is None
+    assert [s for s, _ in lazy] == eager and len(eager) > 350
+    assert len({n for _, n in lazy}) == len(lazy)
+    with pytest.raises(ValueError):      # argument validation still happens at call time, not at first iteration
+        R.get_reads(str(fasta), False, -1, 600, -1, cfg, "expon", 4, "dna-r10-prom", 30, stream=True)
+
+
 def test_fasta_fastq_parser(tmp_path):
     fa = tmp_path / "a.fasta"
     fa.write_text(">r1 desc here\nACGT\nacgtNN\n\n>r2\nTTTT\n>empty\n>r3\tx\nGG\r\nCC\r\n")
