@@ -348,7 +348,9 @@ class _ReadPipeline:
                 off = b["off_host"].numpy()
                 sig = b["slot"].sig.numpy()
                 w = self.m.out_writer
-                if w is not None:      # the views are valid until save() returns (writer plug-point contract)
+                if w is not None and hasattr(w, "save_flat"):
+                    w.save_flat(b["names"], sig, off)      # one contiguous buffer + offsets: no per-read Python work
+                elif w is not None:    # the views are valid until save() returns (writer plug-point contract)
                     w.signals = OrderedDict((name, sig[off[i]:off[i + 1]]) for i, name in enumerate(b["names"]))
                     w.save()
                     w.signals = []

@@ -196,6 +196,60 @@ class BLOW5Writer(_WriterBase):
             _lib.check_blow5(lib.s2s_blow5_close(handle), "s2s_blow5_close")
 
 
+    def save_flat(self, names, flat: np.ndarray, offsets: np.ndarray):
+        """Fast path of the read pipeline: the digitised signals of a batch as ONE contiguous int16 array plus per-read
+        offsets (read i = flat[offsets[i]:offsets[i+1]], in `names` order).  Writes exactly the records that
+        ``signals = {name: flat[...]}; save()`` writes — same numbering, same order of the per-record NumPy draws, empty
+        reads skipped — with the per-read Python work (two scalar draws, a UUID object, a bytes append, a second copy
+        of every signal) replaced by array operations: the writer thread shares the GIL with the read sampler."""
+        n_all = len(names)
+        lens = np.diff(np.asarray(offsets[: n_all + 1], dtype=np.int64))
+        base = self._id_base
+        self._id_base += n_all
+        keep = np.flatnonzero(lens > 0)
+        n = int(keep.size)
+        lib = _lib.load_blow5()
+        filename = str(self.filename)
+        append = os.path.exists(filename)
+        fmt = 1 if filename.endswith(".slow5") else 0
+        handle = C.c_void_p()
+        _lib.check_blow5(lib.s2s_blow5_open(filename.encode(), fmt, int(append), self.record_compression,
+                                            self._header_attrs().encode(), C.byref(handle)), "s2s_blow5_open")
+        try:
+            if n:
+                klens = lens[keep]
+                if n == n_all:       # nothing skipped: the batch buffer is already the concatenation
+                    sig = np.ascontiguousarray(flat[int(offsets[0]):int(offsets[n_all])], dtype=np.int16)
+                else:
+                    sig = np.ascontiguousarray(np.concatenate([flat[int(offsets[i]):int(offsets[i + 1])] for i in keep]),
+                                               dtype=np.int16)
+                out_off = np.zeros(n + 1, dtype=np.int64)
+                np.cumsum(klens, out=out_off[1:])
+                if self.ideal_mode:
+                    med_v = np.full(n, self.median_before, np.float64)
+                    off_v = np.full(n, self.offset, np.float64)
+                else:   # (median_before, offset) per record, in record order: the same stream as n pairs of scalar draws
+                    draws = np.random.normal([self.median_before, self.offset], [self.median_before_std, self.offset_std],
+                                             size=(n, 2))
+                    med_v, off_v = np.ascontiguousarray(draws[:, 0]), np.ascontiguousarray(draws[:, 1])
+                idx = (base + keep).astype(np.int64)
+                if self.preserve_read_ids:
+                    ids = b"".join(str(names[i]).encode() + b"\0" for i in keep)
+                else:
+                    ids = b"".join(b"00000000-0000-0000-0000-%012d\0" % (int(i) + 1) for i in idx)
+                rnum = idx.astype(np.int32)
+                stime = (self.start_time + out_off[:-1]).astype(np.uint64)
+                self.start_time += int(out_off[-1])
+                p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+                _lib.check_blow5(lib.s2s_blow5_write_batch(handle, n, ids, p(sig), p(out_off), p(off_v), p(med_v),
+                                                           p(rnum), p(stime), self.digitisation, self.signal_range,
+                                                           self.sample_rate, self.n_threads), "s2s_blow5_write_batch")
+                self.reads_written += n
+                self.samples_written += int(out_off[-1])
+        finally:
+            _lib.check_blow5(lib.s2s_blow5_close(handle), "s2s_blow5_close")
+
+
 class POD5Writer(_WriterBase):
     """Export signal predictions to a pod5 file (signal_io.py:175-282).  Needs the third-party ``pod5`` package."""
 

@@ -106,3 +106,39 @@ def test_writer_errors_and_kits(tmp_path):
     with pytest.raises(ValueError):
         get_seq_kit_and_flow_cell("dna-r7-min")
     assert str(indexed_uuid(12)) == "00000000-0000-0000-0000-000000000012"
+
+
+@pytest.mark.parametrize("ideal,preserve", [(True, False), (False, False), (False, True)])
+def test_save_flat_equals_dict_save(tmp_path, ideal, preserve):
+    """BLOW5Writer.save_flat (one contiguous int16 buffer + offsets, the read pipeline's fast path) writes byte-identical
+    files to ``signals = {...}; save()``: numbering across batches, empty reads skipped, the per-record NumPy draws in
+    the same order."""
+    from seq2squiggle_b200.profiles import get_profile
+    from seq2squiggle_b200.signal_io import BLOW5Writer
+    prof = get_profile("dna-r10-prom")
+    rng = np.random.default_rng(2)
+    batches = []
+    for b in range(3):
+        lens = rng.integers(0, 400, size=17)
+        lens[rng.integers(0, 17, size=3)] = 0                  # empty reads in the middle and possibly at the ends
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        flat = rng.integers(-300, 1200, size=int(off[-1])).astype(np.int16)
+        batches.append(([f"read-{b}-{i}" for i in range(17)], flat, off))
+    files = []
+    for mode in ("dict", "flat"):
+        w = BLOW5Writer(str(tmp_path / f"{mode}.blow5"), prof, ideal, "dna-r10-prom", preserve)
+        np.random.seed(123)
+        for names, flat, off in batches:
+            if mode == "dict":
+                w.signals = {n: flat[off[i]:off[i + 1]] for i, n in enumerate(names)}
+                w.save()
+            else:
+                w.save_flat(names, flat, off)
+        files.append(open(w.filename, "rb").read())
+        assert w.reads_written == sum(int((np.diff(o) > 0).sum()) for _, _, o in batches)
+    a, b = files
+    # the header carries exp_start_time (wall clock, second resolution): compare everything after it
+    ha = a.index(b"#char*"); hb = b.index(b"#char*")
+    assert a[ha:] == b[hb:]
+    recs = read_blow5(str(tmp_path / "flat.blow5"))["records"]
+    assert [r["read_number"] for r in recs] == [i for i, l in enumerate(np.concatenate([np.diff(o) for _, _, o in batches])) if l > 0]
