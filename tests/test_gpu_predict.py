@@ -114,6 +114,43 @@ def test_predict_reads_equals_predict_step(golden_dir, tmp_path):
     assert sum(len(r["signal"]) for r in a["records"]) > 1000
 
 
+def test_read_pipeline_edge_cases_and_errors(golden_dir, tmp_path):
+    """The staging pipeline behind predict_reads: empty batches, batches with no chunk at all, growth of the recycled
+    slots when a later batch is much larger, reuse across epochs, and a writer exception surfacing at the next call."""
+    from seq2squiggle_b200.model import seq2squiggle
+    path, sd, cfg = _ckpt(golden_dir)
+    kw = dict(dwell_mean=12.5, dwell_std=0.0, noise_std=2.0, noise_sampling=True, duration_sampling=True,
+              export_every_n_samples=10 ** 9, min_noise=0.0, min_duration=3, seed=5)
+    w = _writer(tmp_path, ideal=True, name="edge.blow5")
+    m = seq2squiggle.load_from_checkpoint(path, out_writer=w, **kw)
+    small = [(s, "small_" + n) for s, n in _reads(6, seed=3, lo=40, hi=200)]
+    big = [(s, "big_" + n) for s, n in _reads(40, seed=4, lo=2000, hi=6000)]
+    m.predict_reads([])
+    m.predict_reads([("ACG", "too-short"), ("", "empty")])
+    m.predict_reads(small)
+    m.predict_reads(big)                      # far larger than the first batch: every slot has to grow
+    m.on_predict_epoch_end()
+    m.predict_reads(small[:2])                # second epoch on the same pipeline
+    m.on_predict_epoch_end()
+    f = read_blow5(w.filename)
+    assert [r["read_id"] for r in f["records"]] == [n for _, n in small + big + small[:2]]
+    assert [r["read_number"] for r in f["records"]] == list(range(2, 2 + 48))          # the two chunk-less reads count
+
+    class Boom:
+        profile, profile_name, is_rna = w.profile, "dna-r10-prom", False
+
+        def save(self):
+            raise OSError("disk full")
+    m2 = seq2squiggle.load_from_checkpoint(path, out_writer=Boom(), **kw)
+    m2.predict_reads(small)
+    with pytest.raises(OSError, match="disk full"):
+        m2.on_predict_epoch_end()
+    m2.out_writer = _writer(tmp_path, ideal=True, name="after.blow5")
+    m2.predict_reads(small)                   # the pipeline is usable again after the error was reported
+    m2.on_predict_epoch_end()
+    assert len(read_blow5(m2.out_writer.filename)["records"]) == len(small)
+
+
 def test_writer_digitises_float_pa_on_device(golden_dir, tmp_path):
     """Reference writer contract: signals = {read_id: float pA tensor}; digitised by the CUDA kernel (signal_io.py:134-141)."""
     fx = np.load(os.path.join(golden_dir, "digitise_kat.npz"))
