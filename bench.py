@@ -303,7 +303,7 @@ def run_ours(args):
     line = {"metric": "simulated raw-signal samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else "f32",
-            "data": "synthetic", "config": workload_config(args.reads_per_step, int(os.environ.get("S2S_BATCH_CHUNKS", "0")) or None),
+            "data": "synthetic", "config": workload_config(args.reads_per_step, int(os.environ.get("S2S_BATCH_CHUNKS", "0")) or 32768),
             "reads_per_s": reads / (ms * 1e-3), "chunks_per_s": chunks / (ms * 1e-3),
             "decoder_positions_per_s": 250 * chunks / (ms * 1e-3),
             "model_tflops": FLOP_PER_CHUNK * chunks / (ms * 1e-3) / 1e12,
