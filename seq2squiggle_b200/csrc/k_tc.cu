@@ -461,6 +461,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
                                                       const __grid_constant__ CUtensorMap tmWfc,
                                                       const __grid_constant__ CUtensorMap tmW1,
                                                       const __grid_constant__ CUtensorMap tmW2,
+                                                      const __grid_constant__ CUtensorMap tmXout,
                                                       const float* __restrict__ bfc, const float* __restrict__ g1,
                                                       const float* __restrict__ be1, const float* __restrict__ b1,
                                                       const float* __restrict__ b2, const float* __restrict__ g2,
@@ -468,6 +469,11 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
                                                       __half* __restrict__ x16, const float* __restrict__ w_out,
                                                       const float* __restrict__ b_out, float* __restrict__ p_out,
                                                       int n_tiles, int* status) {
+  // Decoder block with a block output (not the last one): the new fp16 rows leave through shared memory and ONE TMA
+  // store per tile.  A thread's row is 128 contiguous bytes, so direct stores are eight 16-byte pieces at a 128-byte lane
+  // stride: 1,024 separate line transactions per tile, measured at ~1.5 k clk per tile (the out-head variant, which
+  // stores nothing, is 11 % faster).  The staging buffer is the tile's own A buffer, free once W1 has consumed Y.
+  constexpr bool kTmaStore = !kRes32 && !kOutHead;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_w, bar_a[2], bar_m0, bar_m1, bar_m2;
   __shared__ uint32_t s_tmem;
@@ -529,6 +535,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
     uint8_t* sAb = sA + buf * kSlab;
     const int next = tile + gridDim.x;
     if (tid == 0 && next < n_tiles) {  // the other buffer's last reader (W1 MMA of the previous tile) has completed
+      if (kTmaStore && it > 0) tma_store_wait_read();  // ... and so has the TMA store of the previous tile's output
       mbar_arrive_expect_tx(&bar_a[buf ^ 1], kSlab);
       tma_load_2d(sA + (buf ^ 1) * kSlab, &tmA, &bar_a[buf ^ 1], 0, next * 128);
     }
@@ -664,7 +671,17 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
       for (int i = 0; i < 32; ++i) y[c0 + i] += __uint_as_float(r[i]);
     }
     tcgen05_fence_before();
-    layernorm_store<kRes32, !kOutHead>(y, s_v[4], s_v[5], x32 + row * 64, x16 + row * 64);
+    if constexpr (kTmaStore) {
+      layernorm_store<false, false>(y, s_v[4], s_v[5], nullptr, nullptr);   // normalise in registers only
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(sAb + sw128_offset(tid, c)) =
+            make_uint4(pack_half2(y[8 * c], y[8 * c + 1]), pack_half2(y[8 * c + 2], y[8 * c + 3]),
+                       pack_half2(y[8 * c + 4], y[8 * c + 5]), pack_half2(y[8 * c + 6], y[8 * c + 7]));
+      fence_proxy_async_smem();
+    } else {
+      layernorm_store<kRes32, !kOutHead>(y, s_v[4], s_v[5], x32 + row * 64, x16 + row * 64);
+    }
     if (kOutHead) {
       float acc = b_out[0];
 #pragma unroll
@@ -673,8 +690,13 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
     }
     __syncthreads();  // all TMEM reads are done before the next tile's MMA overwrites the accumulators
     tcgen05_fence_after();
+    if (kTmaStore && tid == 0) {
+      tma_store_2d(&tmXout, sAb, 0, tile * 128);
+      tma_store_commit();
+    }
     PHF(7);  // epilogue 3: accumulate, LayerNorm 2, store + closing sync
   }
+  if (kTmaStore && tid == 0) tma_store_wait_all();
   PHF_FLUSH;
   __syncthreads();
   if (warp == 0) tmem_dealloc<256>(tmem);
@@ -902,11 +924,11 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* p_out
       s.prof_chunks += n_chunks;
     }
     if (l + 1 < w.cfg.decoder_layers)
-      k_tc_fc_ffn<false, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, bl.fc_b, bl.ln1_w, bl.ln1_b, bl.b1,
+      k_tc_fc_ffn<false, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.fc_b, bl.ln1_w, bl.ln1_b, bl.b1,
                                                              bl.b2, bl.ln2_w, bl.ln2_b, nullptr, b.x16, nullptr, nullptr,
                                                              nullptr, n_tiles, s.d_status);
     else
-      k_tc_fc_ffn<false, true><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, bl.fc_b, bl.ln1_w, bl.ln1_b, bl.b1,
+      k_tc_fc_ffn<false, true><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.fc_b, bl.ln1_w, bl.ln1_b, bl.b1,
                                                             bl.b2, bl.ln2_w, bl.ln2_b, nullptr, b.x16, w.out_w, w.out_b,
                                                             p_out, n_tiles, s.d_status);
     S2S_LAUNCH_CHECK();
@@ -948,7 +970,7 @@ int tc_encoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, 
     k_tc_qkv_plain<<<grid2, 128, kSmemQkv, st>>>(tmX, tmWqkv, bl.bqkv, qkv16, (int64_t)rows, s.d_status);
     S2S_LAUNCH_CHECK();
     if (launch_attention_enc_f16(qkv16, o16, n_chunks, st)) return -1;
-    k_tc_fc_ffn<true, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, bl.fc_b, bl.ln1_w, bl.ln1_b, bl.b1, bl.b2,
+    k_tc_fc_ffn<true, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.fc_b, bl.ln1_w, bl.ln1_b, bl.b1, bl.b2,
                                                            bl.ln2_w, bl.ln2_b, x32, x16, nullptr, nullptr, nullptr, n_tiles,
                                                            s.d_status);
     S2S_LAUNCH_CHECK();
