@@ -24,7 +24,7 @@ import numpy as np
 
 from .checkpoint import check_model
 from .profiles import get_profile, update_config, update_profile
-from .reads import get_reads
+from .reads import get_reads, get_reads_shard
 from .signal_io import BLOW5Writer, POD5Writer, indexed_uuid
 
 logger = logging.getLogger("seq2squiggle")
@@ -199,23 +199,23 @@ def inference_run(config: dict, saved_weights: str, fasta: str, read_input: bool
         precision=precision)
     check_model(load_model.hparams.config, config)
 
-    # single process: reads are sampled lazily, batch by batch, while the GPU works on the previous batches (the
-    # sampler is sequential Python); the sharded multi-process run needs the whole list to balance the ranks
-    reads, total_l = get_reads(fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len,
-                               stream=(world == 1), cheap_names=not preserve_read_ids)
+    # reads are sampled lazily, batch by batch, while the GPU works on the previous batches (the sampler is
+    # sequential Python); a sharded multi-process run first replays the sampler for the read lengths alone to
+    # balance the ranks by chunk count, then materialises only its own reads (reads.get_reads_shard)
     k = config["seq_kmer"]
     chunk_base = 0
     if world > 1:
         import torch.distributed as dist
         if not dist.is_initialized():
             dist.init_process_group("gloo")      # control plane only: a barrier before the merge
-        reads = list(reads)
-        counts = [chunks_of_read(len(s), k) for s, _ in reads]
-        lo, hi = shard_reads(counts, world)[rank]
-        chunk_base = int(sum(counts[:lo]))
-        logger.info(f"rank {rank}/{world}: reads [{lo}, {hi}) of {len(reads)}, first global chunk {chunk_base}")
-        reads = reads[lo:hi]
+        reads, (lo, hi), n_all, chunk_base = get_reads_shard(
+            fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len, rank, world, shard_reads,
+            chunks_of_read, cheap_names=not preserve_read_ids)
+        logger.info(f"rank {rank}/{world}: reads [{lo}, {hi}) of {n_all}, first global chunk {chunk_base}")
         np.random.seed((seed + rank) % (2 ** 32))  # per-record offset / median_before draws differ per rank
+    else:
+        reads, total_l = get_reads(fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len,
+                                   stream=True, cheap_names=not preserve_read_ids)
     load_model.chunks_done = chunk_base
     n_reads = 0
     for batch in batch_reads(reads, k):

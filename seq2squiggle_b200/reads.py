@@ -223,43 +223,88 @@ def sampling(num_seqs, genome_seqs, genome_lens, r, seed, total_len, distr, prof
 
 
 def sampling_iter(num_seqs, genome_seqs, genome_lens, r, seed, total_len, distr, profile, min_read_len=30,
-                  max_retries=20) -> Generator[str, None, None]:
+                  max_retries=20, window=None, lengths_only=False) -> Generator:
     """``sampling`` as a generator: the same reads in the same order (the same calls on the ``random`` module and the
-    same per-read seeds), produced on demand so that the caller can overlap sampling with the GPU."""
+    same per-read seeds), produced on demand so that the caller can overlap sampling with the GPU.
+
+    ``window=(lo, hi)`` yields only the accepted reads number ``lo <= i < hi`` (a rank's shard) and stops after
+    ``hi``; ``lengths_only`` yields the length of every accepted read instead of the read.  Reads that are not
+    materialised still consume exactly the ``random`` calls the reference would make for them (start position,
+    strand, one ``choice`` per ``N``), so every rank of a sharded run sees the same read list without building it:
+    the acceptance test of ``read_check`` is evaluated on (start, length) and ``str.count`` over the genome span
+    instead of on a slice."""
     draw = DISTR_FUNCS[distr]
     total_genome_len = sum(genome_lens)
     dna = profile.startswith("dna")
+    lo, hi = window if window is not None else (0, None)
     # first-attempt lengths of all reads in one vectorised pass (default law, 32-bit seeds); retries and the other
     # laws take the per-seed path.  Identical values either way.
-    first_len = None
-    if distr == "expon" and r > 0 and num_seqs > 0 and 0 <= seed and seed + num_seqs * (max_retries + 1) < 2 ** 32:
-        first_len = draw_expon_dis_many(r, seed + np.arange(num_seqs, dtype=np.uint64) * np.uint64(max_retries + 1),
-                                        total_len)
+    # (computed block by block on demand: a block's arrays stay in cache and the first read is not held up by the rest)
+    vectorised = distr == "expon" and r > 0 and num_seqs > 0 and 0 <= seed and seed + num_seqs * (max_retries + 1) < 2 ** 32
+    first_len, block0, kBlock = None, 0, 8192
+    has_n = ["N" in g for g in genome_seqs]
+    debug = logger.isEnabledFor(logging.DEBUG)
+    accepted = 0
+    randint, choice = random.randint, random.choice
     for read_i in range(num_seqs):
+        if hi is not None and accepted >= hi:
+            return
         retries = 0
         while retries < max_retries:
-            start_pos = random.randint(0, total_genome_len - 1)
-            genome_index, start_index = get_genome_and_position(genome_lens, start_pos)
-            genome = genome_seqs[genome_index]
-            unique_seed = seed + read_i * (max_retries + 1) + retries
-            if first_len is not None and retries == 0:
-                read_length = first_len[read_i]
+            start_pos = randint(0, total_genome_len - 1)
+            if len(genome_lens) == 1:
+                genome_index, start_index = 0, start_pos
             else:
+                genome_index, start_index = get_genome_and_position(genome_lens, start_pos)
+            genome = genome_seqs[genome_index]
+            if vectorised and retries == 0:
+                if first_len is None or read_i >= block0 + kBlock:
+                    block0 = read_i - read_i % kBlock
+                    idx = np.arange(block0, min(block0 + kBlock, num_seqs), dtype=np.uint64)
+                    first_len = draw_expon_dis_many(r, np.uint64(seed) + idx * np.uint64(max_retries + 1), total_len)
+                read_length = first_len[read_i - block0]
+            else:
+                unique_seed = seed + read_i * (max_retries + 1) + retries
                 read_length = int(draw(r, unique_seed, total_len)) if r > 0 else len(genome)
-            read = genome[start_index:start_index + read_length]
-            read_strand = random.choice("+-") if dna else "+"
-            if read_check(read, read_length, read_i, profile, min_read_len):
-                if "N" in read:
-                    read = N_to_ACTG(read)
-                if read_strand == "-":
-                    read = reverse_complement(read)
-                yield read
+            read_strand = choice("+-") if dna else "+"
+            # read_check (utils.py:381-398) on the span [start_index, start_index + read_length) of the genome
+            got = max(0, min(read_length, len(genome) - start_index))
+            count_n = genome.count("N", start_index, start_index + got) if has_n[genome_index] else 0
+            ok = True
+            if dna and got != read_length:
+                ok = False
+                if debug:
+                    logger.debug(f"Sampled Read length ({got}) of read {read_i} is shorter than real read length ({read_length}).")
+            elif got < min_read_len:
+                ok = False
+                if debug:
+                    logger.debug(f"Sampled Read length ({got}) of read {read_i} is shorter than the minimal read length ({min_read_len}).")
+            elif count_n > 0.1 * read_length:
+                ok = False
+                if debug:
+                    logger.debug(f"Too many 'N' bases ({count_n} out of {read_length}) for read {read_i}")
+            if ok:
+                wanted = accepted >= lo and not lengths_only
+                if wanted:
+                    read = genome[start_index:start_index + got]
+                    if count_n:
+                        read = N_to_ACTG(read)
+                    if read_strand == "-":
+                        read = reverse_complement(read)
+                    yield read
+                else:
+                    for _ in range(count_n):      # N_to_ACTG draws one base per N, in order
+                        choice("ACGT")
+                    if lengths_only:
+                        yield got
+                accepted += 1
                 break
             retries += 1
-            if retries >= max_retries:
-                logger.debug(f"Failed to sample a valid read after {max_retries} retries for read {read_i}. Skipping this read.")
-            else:
-                logger.debug(f"Retrying to sample read {read_i} (attempt {retries + 1}/{max_retries})")
+            if debug:
+                if retries >= max_retries:
+                    logger.debug(f"Failed to sample a valid read after {max_retries} retries for read {read_i}. Skipping this read.")
+                else:
+                    logger.debug(f"Retrying to sample read {read_i} (attempt {retries + 1}/{max_retries})")
 
 
 def export_fasta(read_l: Iterable[str], fasta) -> str:
@@ -272,18 +317,21 @@ def export_fasta(read_l: Iterable[str], fasta) -> str:
     return out_file
 
 
-def yield_reads(reads: Iterable[str], cheap_names: bool = False):
+def yield_reads(reads: Iterable[str], cheap_names: bool = False, first: int = 0):
     """utils.py:489-490: ``(read, uuid4 name)``.  ``cheap_names``: the names are only dictionary keys (the writers
-    replace them with indexed ids unless ``--preserve-read-ids``), so a counter does instead of 100k ``uuid4()`` calls."""
+    replace them with indexed ids unless ``--preserve-read-ids``), so a counter (starting at ``first``, the global
+    index of a shard's first read) does instead of 100k ``uuid4()`` calls."""
     if cheap_names:
-        return ((read, f"read_{i}") for i, read in enumerate(reads))
+        return ((read, f"read_{i}") for i, read in enumerate(reads, first))
     return ((read, str(uuid4())) for read in reads)
 
 
 def sample_reads_from_reference(genome_seqs, genome_lens, n, r, c, config, fasta, seed, save=False, distr="expon",
-                                profile="dna-r10-min", min_read_len=30, stream=False, cheap_names=False):
+                                profile="dna-r10-min", min_read_len=30, stream=False, cheap_names=False, window=None,
+                                lengths_only=False):
     """utils.py:493-582: argument validation (same messages) + sampling.  ``stream``: return a lazy generator (and no
-    length hint) instead of sampling every read up front."""
+    length hint) instead of sampling every read up front; with ``window`` / ``lengths_only`` (see ``sampling_iter``)
+    the generator yields one shard of the reads / the accepted read lengths."""
     logger.debug("Generating reads from the reference input file.")
     if n <= 0 and c <= 0:
         logger.error("You need to specify the coverage c or the number of reads n")
@@ -304,8 +352,11 @@ def sample_reads_from_reference(genome_seqs, genome_lens, n, r, c, config, fasta
             " If the sampled read length is higher than the reference sequence length, they will be skipped."
             " Consider reducing the desired average read length via -r.")
     if stream and not save:
-        return yield_reads(sampling_iter(seq_num, genome_seqs, genome_lens, r, seed, total_len, distr, profile,
-                                         min_read_len), cheap_names), None
+        it = sampling_iter(seq_num, genome_seqs, genome_lens, r, seed, total_len, distr, profile, min_read_len,
+                           window=window, lengths_only=lengths_only)
+        if lengths_only:
+            return it, None
+        return yield_reads(it, cheap_names, first=window[0] if window else 0), None
     read_list = sampling(seq_num, genome_seqs, genome_lens, r, seed, total_len, distr, profile, min_read_len)
     total_l = sum(round(len(read) / config["max_dna_len"]) for read in read_list)
     reads_fasta = export_fasta(read_list, fasta) if save else yield_reads(read_list, cheap_names)
@@ -335,3 +386,37 @@ def get_reads(fasta, read_input, n, r, c, config, distr, seed, profile, min_read
     reads_fasta, total_l = sample_reads_from_reference(genome_seqs, genome_lens, n, r, c, config, fasta, seed, save,
                                                        distr, profile, min_read_len, stream, cheap_names)
     return read_fasta(reads_fasta, is_rna) if save else (reads_fasta, total_l)
+
+
+def get_reads_shard(fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len, rank, world, shard_fn,
+                    chunks_fn, cheap_names=False):
+    """The reads of rank ``rank`` of a ``world``-process run: ``(iterator of (sequence, name), (lo, hi), number of
+    reads of the whole run, global index of the shard's first chunk)``.
+
+    Every rank derives the same read list from the seed (the reference has no sharded predict).  In
+    reference mode the list is never built: a first pass replays the sampler for the accepted read *lengths* only
+    (about 1 us per read), ``shard_fn(chunk counts, world)`` balances the contiguous read ranges by chunk count, and
+    a second pass from the same ``random`` state materialises only this rank's reads, lazily, while the GPU works.
+    Sampling every read on every rank (16 us and 5 kB per read at ``-r 5000``) cost 10 s and 3 GB per rank at
+    BASELINE config 5 (600,000 reads) before the first kernel could start."""
+    k = config["seq_kmer"]
+    if read_input:
+        reads, _ = get_reads(fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len)
+        reads = list(reads)     # read mode samples references to the input reads: nothing to save
+        counts = np.asarray([chunks_fn(len(s), k) for s, _ in reads], dtype=np.int64)
+        lo, hi = shard_fn(counts, world)[rank]
+        return iter(reads[lo:hi]), (lo, hi), len(reads), int(counts[:lo].sum())
+    logger.info("Reference mode.")
+    genome_seqs, genome_lens = preprocess_genome(fasta)
+    state = random.getstate()
+    lens, _ = sample_reads_from_reference(genome_seqs, genome_lens, n, r, c, config, fasta, seed, False, distr, profile,
+                                          min_read_len, stream=True, lengths_only=True)
+    lens = np.fromiter(lens, dtype=np.int64)
+    random.setstate(state)
+    nk = lens - k + 1
+    counts = np.where(nk > 0, -(-nk // config["max_dna_len"]), 0)
+    lo, hi = shard_fn(counts, world)[rank]
+    reads, _ = sample_reads_from_reference(genome_seqs, genome_lens, n, r, c, config, fasta, seed, False, distr,
+                                           profile, min_read_len, stream=True, cheap_names=cheap_names,
+                                           window=(lo, hi))
+    return reads, (lo, hi), len(lens), int(counts[:lo].sum())

@@ -90,6 +90,55 @@ def test_streamed_sampling_equals_eager(tmp_path):
         R.get_reads(str(fasta), False, -1, 600, -1, cfg, "expon", 4, "dna-r10-prom", 30, stream=True)
 
 
+def test_sharded_sampling_equals_eager(tmp_path):
+    """get_reads_shard (what a torchrun rank uses): the shards of all ranks, concatenated, are the eager read list —
+    although no rank materialises another rank's reads — the ``random`` state after a full replay is the eager one,
+    and the first-chunk indices are the running chunk totals.  Genome with N runs and three contigs, DNA and RNA."""
+    import random
+    from seq2squiggle_b200 import reads as R
+    from seq2squiggle_b200.inference import chunks_of_read, shard_reads
+    rng = np.random.default_rng(12)
+    contigs = ["".join(rng.choice(list("ACGTN"), n, p=[0.24, 0.24, 0.24, 0.24, 0.04])) for n in (9000, 20000, 4000)]
+    fasta = tmp_path / "g.fasta"
+    fasta.write_text("".join(f">c{i}\n{g}\n" for i, g in enumerate(contigs)))
+    cfg = {"max_dna_len": 16, "seq_kmer": 9}
+    for profile in ("dna-r10-prom", "rna-004-prom"):
+        random.seed(6)
+        eager = [s for s, _ in R.get_reads(str(fasta), False, 500, 700, -1, cfg, "expon", 6, profile, 30)[0]]
+        after_eager = random.random()
+        assert 400 < len(eager) <= 500
+        counts = [chunks_of_read(len(s), 9) for s in eager]
+        for world in (1, 2, 3, 8):
+            got, bases = [], []
+            for rank in range(world):
+                random.seed(6)
+                it, (lo, hi), n_all, base = R.get_reads_shard(str(fasta), False, 500, 700, -1, cfg, "expon", 6, profile,
+                                                              30, rank, world, shard_reads, chunks_of_read,
+                                                              cheap_names=True)
+                mine = list(it)
+                assert n_all == len(eager) and len(mine) == hi - lo and base == sum(counts[:lo])
+                assert [n for _, n in mine] == [f"read_{i}" for i in range(lo, hi)]
+                got += [s for s, _ in mine]
+                bases.append(base)
+            assert got == eager and bases == sorted(bases)
+        # lengths-only replay: same lengths, same generator state afterwards
+        random.seed(6)
+        seqs, lens = R.preprocess_genome(str(fasta))
+        ln = list(R.sampling_iter(500, seqs, lens, 700, 6, sum(lens), "expon", profile, lengths_only=True))
+        assert ln == [len(s) for s in eager] and random.random() == after_eager
+    # read mode shards the sampled list
+    rd = tmp_path / "reads.fasta"
+    rd.write_text("".join(f">r{i}\n{'ACGT' * (10 + 7 * i)}\n" for i in range(6)))
+    full = [s for s, _ in R.get_reads(str(rd), True, 40, 0, -1, cfg, "expon", 3, "dna-r10-prom", 30)[0]]
+    parts = []
+    for rank in range(3):
+        it, (lo, hi), n_all, base = R.get_reads_shard(str(rd), True, 40, 0, -1, cfg, "expon", 3, "dna-r10-prom", 30, rank,
+                                                      3, shard_reads, chunks_of_read)
+        parts += [s for s, _ in it]
+        assert n_all == 40
+    assert parts == full
+
+
 def test_fasta_fastq_parser(tmp_path):
     fa = tmp_path / "a.fasta"
     fa.write_text(">r1 desc here\nACGT\nacgtNN\n\n>r2\nTTTT\n>empty\n>r3\tx\nGG\r\nCC\r\n")
