@@ -462,13 +462,13 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
                                                       const __grid_constant__ CUtensorMap tmW1,
                                                       const __grid_constant__ CUtensorMap tmW2,
                                                       const __grid_constant__ CUtensorMap tmXout,
-                                                      const float* __restrict__ bfc, const float* __restrict__ g1,
-                                                      const float* __restrict__ be1, const float* __restrict__ b1,
-                                                      const float* __restrict__ b2, const float* __restrict__ g2,
-                                                      const float* __restrict__ be2, float* __restrict__ x32,
-                                                      __half* __restrict__ x16, const float* __restrict__ w_out,
-                                                      const float* __restrict__ b_out, float* __restrict__ p_out,
+                                                      const __grid_constant__ FfnParams P, float* __restrict__ x32,
+                                                      __half* __restrict__ x16, float* __restrict__ p_out,
                                                       int n_tiles, int* status) {
+  // The per-column vectors (three biases, two LayerNorm affine pairs, out_linear) arrive as a __grid_constant__ kernel
+  // parameter: every use below has a compile-time index, so they are constant-bank operands of the FADD / FFMA itself
+  // (c[0x0][imm]) instead of ~180 LDS.128 per row from a shared-memory copy whose latency the two warps per scheduler
+  // could not hide (short-scoreboard stalls were 1.1 per issued instruction, profiles/r01_ffn_ncu.txt).
   // Decoder block with a block output (not the last one): the new fp16 rows leave through shared memory and ONE TMA
   // store per tile.  A thread's row is 128 contiguous bytes, so direct stores are eight 16-byte pieces at a 128-byte lane
   // stride: 1,024 separate line transactions per tile, measured at ~1.5 k clk per tile (the out-head variant, which
@@ -478,8 +478,6 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
   __shared__ __align__(8) uint64_t bar_w, bar_a[2], bar_m0, bar_m1, bar_m2;
   __shared__ uint32_t s_tmem;
   __shared__ int s_abort, s_go;
-  __shared__ float s_b1[256], s_v[6][64];  // bfc, g1, be1, b2, g2, be2
-  __shared__ float s_wout[64];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* sW1 = smem;                       // [256 x 128 B]
   uint8_t* sW2 = smem + 2 * kSlab;           // 4 K-slabs x [64 x 128 B]
@@ -496,12 +494,6 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
     fence_mbar_init();
     s_abort = 0;
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmWfc); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
-  }
-  for (int i = tid; i < 256; i += 128) s_b1[i] = b1[i];
-  if (tid < 64) {
-    s_v[0][tid] = bfc[tid]; s_v[1][tid] = g1[tid]; s_v[2][tid] = be1[tid];
-    s_v[3][tid] = b2[tid]; s_v[4][tid] = g2[tid]; s_v[5][tid] = be2[tid];
-    s_wout[tid] = kOutHead ? w_out[tid] : 0.f;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -556,8 +548,8 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         float4 x = rp[i];
-        y[4 * i] = x.x + s_v[0][4 * i]; y[4 * i + 1] = x.y + s_v[0][4 * i + 1];
-        y[4 * i + 2] = x.z + s_v[0][4 * i + 2]; y[4 * i + 3] = x.w + s_v[0][4 * i + 3];
+        y[4 * i] = x.x + P.bfc[4 * i]; y[4 * i + 1] = x.y + P.bfc[4 * i + 1];
+        y[4 * i + 2] = x.z + P.bfc[4 * i + 2]; y[4 * i + 3] = x.w + P.bfc[4 * i + 3];
       }
     } else {
       // the row was fetched one tile ahead (xr): a thread's 128-byte row is eight scattered 16-byte loads whose DRAM
@@ -569,8 +561,8 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[j]));
-          y[8 * i + 2 * j] = f.x + s_v[0][8 * i + 2 * j];
-          y[8 * i + 2 * j + 1] = f.y + s_v[0][8 * i + 2 * j + 1];
+          y[8 * i + 2 * j] = f.x + P.bfc[8 * i + 2 * j];
+          y[8 * i + 2 * j + 1] = f.y + P.bfc[8 * i + 2 * j + 1];
         }
       }
       if (next < n_tiles) {  // tile `next` is only ever touched by this CTA: its rows are still the block input
@@ -601,7 +593,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
       for (int i = 0; i < 64; ++i) { float d = y[i] - mean; var = fmaf(d, d, var); }
       const float rstd = 1.0f / sqrtf(var * (1.f / 64.f) + 1e-5f);
 #pragma unroll
-      for (int i = 0; i < 64; ++i) y[i] = (y[i] - mean) * rstd * s_v[1][i] + s_v[2][i];
+      for (int i = 0; i < 64; ++i) y[i] = (y[i] - mean) * rstd * P.g1[i] + P.be1[i];
 #pragma unroll
       for (int c = 0; c < 8; ++c)
         *reinterpret_cast<uint4*>(sAb + sw128_offset(tid, c)) =
@@ -633,15 +625,15 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          pk[i] = pack_half2_relu(__uint_as_float(r[2 * i]) + s_b1[c * 32 + 2 * i],
-                                  __uint_as_float(r[2 * i + 1]) + s_b1[c * 32 + 2 * i + 1]);
+          pk[i] = pack_half2_relu(__uint_as_float(r[2 * i]) + P.b1[c * 32 + 2 * i],
+                                  __uint_as_float(r[2 * i + 1]) + P.b1[c * 32 + 2 * i + 1]);
         tmem_st_32x16(lane_addr + c * 16, pk);
         tmem_wait_ld();
         if (c + 2 < 8) tmem_ld_32x32(lane_addr + (c + 2) * 32, r);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          pk[i] = pack_half2_relu(__uint_as_float(rb[2 * i]) + s_b1[(c + 1) * 32 + 2 * i],
-                                  __uint_as_float(rb[2 * i + 1]) + s_b1[(c + 1) * 32 + 2 * i + 1]);
+          pk[i] = pack_half2_relu(__uint_as_float(rb[2 * i]) + P.b1[(c + 1) * 32 + 2 * i],
+                                  __uint_as_float(rb[2 * i + 1]) + P.b1[(c + 1) * 32 + 2 * i + 1]);
         tmem_st_32x16(lane_addr + (c + 1) * 16, pk);
         if (c + 2 < 8) tmem_wait_ld();
       }
@@ -659,7 +651,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
       umma_commit(&bar_m2);
     }
 #pragma unroll
-    for (int i = 0; i < 64; ++i) y[i] += s_v[3][i];
+    for (int i = 0; i < 64; ++i) y[i] += P.b2[i];
     wait_bar(&bar_m2, ph, status, &s_abort, kErrFfnMma2);
     tcgen05_fence_after();
     PHF(6);  // sync + W2 issue + wait W2 MMA
@@ -672,7 +664,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
     }
     tcgen05_fence_before();
     if constexpr (kTmaStore) {
-      layernorm_store<false, false>(y, s_v[4], s_v[5], nullptr, nullptr);   // normalise in registers only
+      layernorm_store<false, false>(y, P.g2, P.be2, nullptr, nullptr);   // normalise in registers only
 #pragma unroll
       for (int c = 0; c < 8; ++c)
         *reinterpret_cast<uint4*>(sAb + sw128_offset(tid, c)) =
@@ -680,12 +672,12 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
                        pack_half2(y[8 * c + 4], y[8 * c + 5]), pack_half2(y[8 * c + 6], y[8 * c + 7]));
       fence_proxy_async_smem();
     } else {
-      layernorm_store<kRes32, !kOutHead>(y, s_v[4], s_v[5], x32 + row * 64, x16 + row * 64);
+      layernorm_store<kRes32, !kOutHead>(y, P.g2, P.be2, x32 + row * 64, x16 + row * 64);
     }
     if (kOutHead) {
-      float acc = b_out[0];
+      float acc = P.bout;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) acc = fmaf(y[i], s_wout[i], acc);
+      for (int i = 0; i < 64; ++i) acc = fmaf(y[i], P.wout[i], acc);
       p_out[row] = fmaxf(acc, 0.f);
     }
     __syncthreads();  // all TMEM reads are done before the next tile's MMA overwrites the accumulators
@@ -924,13 +916,11 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* p_out
       s.prof_chunks += n_chunks;
     }
     if (l + 1 < w.cfg.decoder_layers)
-      k_tc_fc_ffn<false, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.fc_b, bl.ln1_w, bl.ln1_b, bl.b1,
-                                                             bl.b2, bl.ln2_w, bl.ln2_b, nullptr, b.x16, nullptr, nullptr,
-                                                             nullptr, n_tiles, s.d_status);
+      k_tc_fc_ffn<false, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, nullptr, b.x16, nullptr,
+                                                             n_tiles, s.d_status);
     else
-      k_tc_fc_ffn<false, true><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.fc_b, bl.ln1_w, bl.ln1_b, bl.b1,
-                                                            bl.b2, bl.ln2_w, bl.ln2_b, nullptr, b.x16, w.out_w, w.out_b,
-                                                            p_out, n_tiles, s.d_status);
+      k_tc_fc_ffn<false, true><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, nullptr, b.x16, p_out,
+                                                            n_tiles, s.d_status);
     S2S_LAUNCH_CHECK();
   }
   return 0;
@@ -970,8 +960,7 @@ int tc_encoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, 
     k_tc_qkv_plain<<<grid2, 128, kSmemQkv, st>>>(tmX, tmWqkv, bl.bqkv, qkv16, (int64_t)rows, s.d_status);
     S2S_LAUNCH_CHECK();
     if (launch_attention_enc_f16(qkv16, o16, n_chunks, st)) return -1;
-    k_tc_fc_ffn<true, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.fc_b, bl.ln1_w, bl.ln1_b, bl.b1, bl.b2,
-                                                           bl.ln2_w, bl.ln2_b, x32, x16, nullptr, nullptr, nullptr, n_tiles,
+    k_tc_fc_ffn<true, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, x32, x16, nullptr, n_tiles,
                                                            s.d_status);
     S2S_LAUNCH_CHECK();
   }

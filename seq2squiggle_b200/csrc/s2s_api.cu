@@ -432,6 +432,14 @@ int s2s_create(const float* weights_host, int64_t n_weights, const s2s_config* c
   d.out_w = f + o_out_w; d.out_b = f + o_out_b;
   for (int i = 0; i < cfg->encoder_layers; ++i) bind_block(d.enc[i], eo[i], f, h->d_f16);
   for (int i = 0; i < cfg->decoder_layers; ++i) bind_block(d.dec[i], dofs[i], f, h->d_f16);
+  auto fill_ffn = [&](FfnParams& p, const BlockW& b) {   // host copy of the per-column vectors (kernel parameter)
+    memcpy(p.bfc, b.fc_b, 64 * 4); memcpy(p.g1, b.ln1_w, 64 * 4); memcpy(p.be1, b.ln1_b, 64 * 4);
+    memcpy(p.b1, b.b1, 256 * 4); memcpy(p.b2, b.b2, 64 * 4); memcpy(p.g2, b.ln2_w, 64 * 4); memcpy(p.be2, b.ln2_b, 64 * 4);
+    memcpy(p.wout, W.out_w, 64 * 4);
+    p.bout = W.out_b[0];
+  };
+  for (int i = 0; i < cfg->encoder_layers; ++i) fill_ffn(d.enc[i].ffn, W.enc[i]);
+  for (int i = 0; i < cfg->decoder_layers; ++i) fill_ffn(d.dec[i].ffn, W.dec[i]);
   if (tc_init(h->tc, h->dw, device)) {
     s2s_destroy(h);
     return -1;

@@ -5,8 +5,17 @@
 
 namespace s2s {
 
+// Per-column vectors of one FFT block's fc + LayerNorm + FFN + LayerNorm tail, passed to k_tc_fc_ffn BY VALUE as a
+// __grid_constant__ kernel parameter (constant-bank operands).  wout / bout: out_linear (modules.py:140) — every
+// decoder block carries a copy, only the last block's kernel reads it.
+struct FfnParams {
+  float bfc[64], g1[64], be1[64], b1[256], b2[64], g2[64], be2[64], wout[64];
+  float bout;
+};
+
 // Device-resident derived weights, built once by s2s_create().
 struct BlockDev {
+  FfnParams ffn;               // host copy (kernel parameter)
   // fp32, transposed to [K][N] so a warp reads consecutive output columns (SIMT path)
   const float *wqkv_t, *bqkv;  // [64][192], [192]   (q | k | v)
   const float *fc_t, *fc_b;    // [64][64]

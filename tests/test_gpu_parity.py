@@ -445,3 +445,64 @@ def test_attention_overflow_falls_back_to_exact_kernel(golden_dir, scale):
                            dwell_mean=12.5, min_duration=3).numpy()
     assert np.abs(a - b).max() <= 0.02 * max(16.5, np.abs(b).max()), np.abs(a - b).max()
     print(f"scale {scale}: flagged units: {flagged} of {4 * codes.shape[0]}; max |fast - exact| = {np.abs(a - b).max():.4g}; oracle row0 max {ref.max():.3g}")
+
+
+def test_fp16_path_against_the_reference_gpu_mode(golden_dir):
+    """The reference's own GPU mode is Lightning ``precision="16-mixed"`` (inference.py:404): fp16 autocast of the ATen
+    ops.  Run the oracle's encoder / decoder (the same ATen calls in the same order as layers.py / modules.py) on the
+    B200 under ``torch.autocast(float16)`` on a golden batch and compare three ways: our tensor-core path and the
+    reference's GPU mode must both sit within the stated tolerance of the fp32 golden vectors, and of each other
+    (2 x the bound: two independent fp16 roundings).  Also times that eager path (the "beat this" number
+    next to the CPU baseline) and leaves the figure in gpurun_out/ when that directory exists."""
+    import time
+    fx = np.load(os.path.join(golden_dir, "predict_k9_ideal.npz"))
+    eng, sd, cfg = _engine(golden_dir, "ckpt_k9_seed1.ckpt")
+    o = json.loads(str(fx["opts"]))
+    opts = _opts(str(fx["profile"]), "fp16", dwell_mean=o["dwell_mean"])
+    codes = torch.from_numpy(fx["codes"]).to("cuda")
+    pa, _ = eng.forward_chunks(codes, opts, taps=True)
+    ours = pa.cpu().numpy()
+
+    sd_dev = {k: v.to("cuda") for k, v in sd.items() if torch.is_tensor(v)}
+    k = cfg["seq_kmer"]
+    onehot = torch.nn.functional.one_hot(codes.long(), 5).to(torch.float16)        # [B,16,k,5], "_ACGT" -> 0..4
+    data = onehot.reshape(onehot.shape[0], 16, 5 * k)
+    j = torch.from_numpy(orc.lr_expand_indices(fx["dur_i"], 250)).to("cuda").long()
+
+    def eager(x):
+        with torch.inference_mode(), torch.autocast("cuda", dtype=torch.float16):
+            enc, _ = orc.encoder_forward(sd_dev, cfg, x)
+            jj = j[: x.shape[0]]
+            lr = torch.where(jj[..., None] >= 0, torch.gather(enc.float(), 1, jj.clamp(min=0)[..., None].expand(-1, -1, 64)), 0.0)
+            return orc.decoder_forward(sd_dev, cfg, lr).squeeze(-1).float() * 165.0
+
+    ref16 = eager(data).cpu().numpy()
+    gold = fx["pA"]
+    _check_pa(ours, gold, "fp16", "ours vs fp32 golden")
+    _check_pa(ref16, gold, "fp16", "reference GPU mode (fp16 autocast) vs fp32 golden")
+    bound = 2 * PA_RTOL_TC * np.maximum(np.abs(gold), PA_FLOOR_TC)
+    assert (np.abs(ours - ref16) / bound).max() <= 1.0
+    e_ours, e_ref = np.abs(ours - gold).max(), np.abs(ref16 - gold).max()
+
+    # eager fp16-autocast throughput of the same modules on this GPU, 1024-chunk batches (--predict-batch-size default)
+    reps = -(-1024 // data.shape[0])
+    batch = data.repeat(reps, 1, 1)[:1024]
+    j = j.repeat(reps, 1)[:1024]
+    for _ in range(3):
+        eager(batch)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_it = 10
+    for _ in range(n_it):
+        eager(batch)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / n_it
+    line = {"what": "oracle encoder+decoder under torch.autocast(fp16) on cuda:0 (the reference's GPU mode, model only: "
+                    "no tokeniser, no writer)", "batch_chunks": 1024, "ms_per_batch": dt * 1e3,
+            "chunks_per_s": 1024 / dt, "decoder_positions_per_s": 256000 / dt,
+            "max_abs_err_vs_fp32_golden_pA": {"ours_fp16": float(e_ours), "autocast_fp16": float(e_ref)}}
+    print(json.dumps(line))
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "eager_gpu_reference_mode.json"), "w") as f:
+            json.dump(line, f)

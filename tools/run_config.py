@@ -7,6 +7,9 @@ box, so a synthetic genome of the same length (or ``--genome-len``) is written f
   gpurun -- python tools/run_config.py --config 2 --n 20000        (read mode, 10 ragged reads sampled n times)
   gpurun -- python tools/run_config.py --config 3 --n 100000       (dna-r9-min, k = 6)
   gpurun -- python tools/run_config.py --config 4 --genome-len 100000000 --c 1 --r 5000
+  gpurun --gpus 2 -- python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+         tools/run_config.py --config 4 --genome-len 100000000 --coverage 3 --read-length 5000 --out /tmp/sim.blow5
+         (read-sharded; torchrun's own parser claims abbreviations such as --r, hence the long spellings)
 """
 import argparse
 import os
@@ -61,8 +64,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, default=1)
     ap.add_argument("--n", type=int, default=100000)
-    ap.add_argument("--c", type=int, default=-1)
-    ap.add_argument("--r", type=int, default=1000)
+    ap.add_argument("--c", "--coverage", dest="c", type=int, default=-1)
+    ap.add_argument("--r", "--read-length", dest="r", type=int, default=1000)
     ap.add_argument("--genome-len", type=int, default=48502)
     ap.add_argument("--out", default=None, help="output file (default: a temporary .blow5; /dev/null is not seekable)")
     ap.add_argument("--seed", type=int, default=11)
@@ -106,6 +109,9 @@ def main():
                             offset_mean=None, offset_std=None, median_before_mean=None, median_before_std=None,
                             min_noise=0.0, min_duration=3, min_read_len=30, preserve_read_ids=False, seed=a.seed)
     wall = time.perf_counter() - t0
+    if int(os.environ.get("RANK", "0")) != 0:      # sharded run: rank 0 holds the merged file and reports
+        print(f"rank {os.environ['RANK']}: {wall:.2f} s wall; " + "; ".join(f"{k.split(' (')[0]} {v:.2f} s" for k, v in T.items()))
+        return
     if prof:
         import pstats
         prof.disable()
