@@ -167,7 +167,7 @@ def run_reference(args):
             "reads_per_s": tot_r / tot_t, "chunks_per_s": tot_c / tot_t,
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit_result(line)
 
 
 def workload_config(reads_per_step, batch_chunks):
@@ -340,7 +340,7 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": n / t, "unit": "samples/s", "cores": cores, "kind": "port",
                                 "sample": f"{args.ref_reads} reads ({c} chunks) of the same distribution, oracle port "
                                           f"of the reference CPU path incl. its Python tokeniser, {t:.1f} s"}
-    print(json.dumps(line))
+    emit_result(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -367,6 +367,18 @@ def kernel_timing(eng, lib, step, i):
             "share": ms.value / e0.elapsed_time(e1)}
 
 
+_RESULT_FD = None
+
+
+def emit_result(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -380,6 +392,13 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    # stdout carries exactly ONE line, the JSON result.  Libraries write there too (NCCL prints "NCCL version ..." to
+    # stdout whatever NCCL_DEBUG_FILE says), so file descriptor 1 is pointed at stderr for the whole run and the result
+    # line goes to the saved descriptor.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -9,8 +9,11 @@ and the file writer overlapped.
 Multi-GPU (``torchrun --nproc-per-node N -m seq2squiggle_b200 predict ...``): one process per GPU.  Every rank
 derives the same read list from the seed, takes a contiguous range of reads balanced by chunk count
 (``shard_reads``), keys its Philox draws by the *global* chunk index (results do not depend on N) and writes
-``<stem>.part<rank>.blow5``; rank 0 stitches the parts into ``<out>`` (``merge_blow5_parts``).  No collective touches the
-data path; the only communication is a barrier on the control-plane process group.
+``<stem>.part<rank>.blow5`` with its GLOBAL read numbers / ids.  At the end rank 0's part becomes ``<out>`` and every
+other rank splices its own records into it at its byte offset, all ranks in parallel (``splice_blow5_part``: kernel
+``copy_file_range`` + a vectorised ``start_time`` shift), instead of one rank re-writing the whole output record by
+record (``merge_blow5_parts``, kept as the stand-alone tool).  No collective touches the data path; the only
+communication is one small all-gather (bytes and samples per rank) and two barriers on the gloo control plane.
 """
 from __future__ import annotations
 
@@ -140,6 +143,104 @@ def merge_blow5_parts(out: str, parts: Sequence[str], preserve_read_ids: bool) -
     return reads_total, samples_total
 
 
+def blow5_record_span(path: str) -> Tuple[int, int]:
+    """``(first byte of the first record, byte after the last record)`` of an uncompressed BLOW5 file."""
+    with open(path, "rb") as f:
+        head = f.read(64)
+        if head[:6] != b"BLOW5\x01":
+            raise ValueError(f"{path} is not a BLOW5 file")
+        if head[9] != 0:
+            raise ValueError("splicing BLOW5 parts needs uncompressed records")
+        (hsize,) = struct.unpack("<I", f.read(4))
+        f.seek(0, os.SEEK_END)
+        end = f.tell()
+        f.seek(end - 5)
+        if f.read(5) != b"5WOLB":
+            raise ValueError(f"{path} has no end-of-file marker (writer not closed?)")
+    return 64 + 4 + hsize, end - 5
+
+
+def splice_blow5_part(out: str, part: str, dst_offset: int, start_time_shift: int) -> int:
+    """Copies the records of ``part`` into ``out`` at byte ``dst_offset`` and adds ``start_time_shift`` (the samples
+    written by the ranks before this one) to every record's ``start_time`` — the last eight bytes of a record, as in
+    ``merge_blow5_parts``.  Run by every rank > 0 at the same time on disjoint byte ranges of ``out``.  The bulk copy is
+    ``os.copy_file_range`` (in-kernel; falls back to read + pwrite), the shift one gather / add / scatter over a memory
+    map of the part file (which is modified).  Returns the number of records."""
+    lo, hi = blow5_record_span(part)
+    n_bytes = hi - lo
+    if n_bytes == 0:
+        return 0
+    src = os.open(part, os.O_RDONLY)
+    try:
+        ends, pos = [], lo                                   # record boundaries from the 8-byte size prefixes
+        while pos < hi:
+            (size,) = struct.unpack("<Q", os.pread(src, 8, pos))
+            pos += 8 + size
+            ends.append(pos - lo)
+    finally:
+        os.close(src)
+    if pos != hi:
+        raise ValueError(f"{part}: records do not end at the end-of-file marker")
+    if start_time_shift:     # patched in the rank's own part file, before the copy: no page of `out` is shared between ranks
+        mm = np.memmap(part, dtype=np.uint8, mode="r+", offset=lo, shape=(n_bytes,))
+        idx = (np.asarray(ends, dtype=np.int64) - 8)[:, None] + np.arange(8, dtype=np.int64)[None, :]
+        st = np.ascontiguousarray(mm[idx]).view("<u8")[:, 0] + np.uint64(start_time_shift)
+        mm[idx] = st.astype("<u8").view(np.uint8).reshape(-1, 8)
+        mm.flush()
+        del mm
+    src = os.open(part, os.O_RDONLY)
+    dst = os.open(out, os.O_RDWR)
+    try:
+        done = 0
+        use_cfr = hasattr(os, "copy_file_range")
+        while done < n_bytes:
+            want = min(n_bytes - done, 1 << 30)
+            if use_cfr:
+                try:
+                    got = os.copy_file_range(src, dst, want, lo + done, dst_offset + done)
+                    if got <= 0:
+                        raise OSError("copy_file_range copied nothing")
+                    done += got
+                    continue
+                except OSError:
+                    use_cfr = False                          # e.g. across file systems on an old kernel
+            buf = os.pread(src, min(want, 64 << 20), lo + done)
+            os.pwrite(dst, buf, dst_offset + done)
+            done += len(buf)
+    finally:
+        os.close(src)
+        os.close(dst)
+    return len(ends)
+
+
+def splice_parts_collective(out: str, my_part: str, rank: int, world: int, my_samples: int, dist) -> Tuple[int, int]:
+    """The end of a sharded run, called by every rank once its writer has closed ``my_part``: rank 0's part becomes
+    ``out`` (a rename), the others splice their records in at their byte offsets at the same time.  The parts carry
+    global read numbers / ids already (``writer._id_base`` = the shard's first read); only ``start_time``, a running sum
+    over all earlier reads of the run, needs the totals of the earlier ranks.  Returns (bytes, samples) of ``out``."""
+    lo, hi = blow5_record_span(my_part)
+    info = [None] * world
+    dist.all_gather_object(info, (hi - lo, int(my_samples), lo))
+    body = [b for b, _, _ in info]
+    samples = [n for _, n, _ in info]
+    first = info[0][2]                                       # the kept header is rank 0's
+    total = first + sum(body) + 5
+    if rank == 0:
+        os.replace(my_part, out)
+        with open(out, "r+b") as f:
+            f.truncate(total)                                # drops rank 0's end marker / reserves the other ranks' ranges
+    dist.barrier()
+    if rank > 0:
+        splice_blow5_part(out, my_part, first + sum(body[:rank]), sum(samples[:rank]))
+        os.remove(my_part)
+    dist.barrier()
+    if rank == 0:
+        with open(out, "r+b") as f:
+            f.seek(total - 5)
+            f.write(b"5WOLB")
+    return total, sum(samples)
+
+
 def part_path(out: str, rank: int) -> str:
     """Per-rank part file of a multi-GPU run: ``sim.blow5`` -> ``sim.part<rank>.blow5`` (keeps the extension, so the
     writer factory's extension check applies to it as to any output)."""
@@ -212,6 +313,7 @@ def inference_run(config: dict, saved_weights: str, fasta: str, read_input: bool
             fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len, rank, world, shard_reads,
             chunks_of_read, cheap_names=not preserve_read_ids)
         logger.info(f"rank {rank}/{world}: reads [{lo}, {hi}) of {n_all}, first global chunk {chunk_base}")
+        writer._id_base = lo                       # read_number / synthetic read ids are global from the start
         np.random.seed((seed + rank) % (2 ** 32))  # per-record offset / median_before draws differ per rank
     else:
         reads, total_l = get_reads(fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len,
@@ -230,12 +332,8 @@ def inference_run(config: dict, saved_weights: str, fasta: str, read_input: bool
         if not os.path.exists(my_out):           # a rank without reads still contributes an (empty) part
             writer.signals = {}
             writer.save()
-        dist.barrier()
+        nbytes, ns = splice_parts_collective(out, my_out, rank, world, writer.samples_written, dist)
         if rank == 0:
-            parts = [part_path(out, i) for i in range(world)]
-            nr, ns = merge_blow5_parts(out, parts, preserve_read_ids)
-            for p in parts:
-                os.remove(p)
-            logger.info(f"merged {world} parts: {nr} reads, {ns} samples -> {out}")
+            logger.info(f"spliced {world} parts: {ns} samples, {nbytes} bytes -> {out}")
         dist.barrier()
     return stats

@@ -1,5 +1,6 @@
 """world_size-2 CPU (gloo) test of the multi-GPU host logic of inference_run: every rank derives the same read list
-from the seed, takes its shard_reads() range, writes a BLOW5 part, rank 0 merges after the barrier.  The device call
+from the seed, takes its shard_reads() range, writes a BLOW5 part with global read numbers, and all ranks splice
+their parts into the output in parallel (splice_parts_collective).  The device call
 is replaced by a deterministic stand-in keyed by the GLOBAL chunk index (exactly what the Philox keying guarantees
 on the GPU), so the merged file must equal the single-process file record for record."""
 import os
@@ -15,7 +16,7 @@ WORKER = textwrap.dedent("""
     import numpy as np
     import torch.distributed as dist
     sys.path.insert(0, %(root)r)
-    from seq2squiggle_b200.inference import chunks_of_read, get_writer, merge_blow5_parts, part_path, shard_reads
+    from seq2squiggle_b200.inference import chunks_of_read, get_writer, part_path, shard_reads, splice_parts_collective
     from seq2squiggle_b200.profiles import get_profile
     from seq2squiggle_b200.reads import sampling
     from seq2squiggle_b200.signal_io import BLOW5Writer
@@ -44,12 +45,12 @@ WORKER = textwrap.dedent("""
     prof = get_profile("dna-r10-prom")
     path = out if world == 1 else part_path(out, rank)
     w, _ = get_writer(path, prof, True, 1000000, "dna-r10-prom", False)   # the same factory (and extension check) as inference_run
+    w._id_base = lo                                # as inference_run: global read numbers / ids from the start
     w.signals = sig
     w.save()
     if world > 1:
-        dist.barrier()
-        if rank == 0:
-            merge_blow5_parts(out, [part_path(out, i) for i in range(world)], False)
+        splice_parts_collective(out, path, rank, world, w.samples_written, dist)
+        assert not os.path.exists(path)
         dist.barrier()
         dist.destroy_process_group()
 """)
@@ -63,7 +64,11 @@ def _free_port():
     return p
 
 
-def test_two_rank_sharded_run_equals_single_process(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_run_equals_single_process(tmp_path, world):
     from tests.blow5_reader import read_blow5
     script = tmp_path / "worker.py"
     script.write_text(WORKER % {"root": ROOT})
@@ -71,12 +76,21 @@ def test_two_rank_sharded_run_equals_single_process(tmp_path):
     subprocess.run([sys.executable, str(script), str(tmp_path / "one.blow5")], check=True, env=env, timeout=300)
     port = _free_port()
     procs = []
-    for r in range(2):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
                    MASTER_PORT=str(port))
-        procs.append(subprocess.Popen([sys.executable, str(script), str(tmp_path / "two.blow5")], env=env))
+        procs.append(subprocess.Popen([sys.executable, str(script), str(tmp_path / "many.blow5")], env=env))
     for p in procs:
         assert p.wait(timeout=300) == 0
-    a, b = read_blow5(str(tmp_path / "one.blow5")), read_blow5(str(tmp_path / "two.blow5"))
+    a, b = read_blow5(str(tmp_path / "one.blow5")), read_blow5(str(tmp_path / "many.blow5"))
     assert len(a["records"]) == len(b["records"]) > 40
     assert a["records"] == b["records"]
+    # byte-identical records and one end marker (the header carries the wall-clock exp_start_time of each run)
+    from seq2squiggle_b200.inference import blow5_record_span
+    blobs = []
+    for name in ("one.blow5", "many.blow5"):
+        lo, hi = blow5_record_span(str(tmp_path / name))
+        data = open(tmp_path / name, "rb").read()
+        assert len(data) == hi + 5
+        blobs.append(data[lo:])
+    assert blobs[0] == blobs[1]

@@ -189,3 +189,57 @@ def test_merge_blow5_parts_equals_single_writer(tmp_path):
     a, b = read_blow5(str(tmp_path / "single.blow5")), read_blow5(str(tmp_path / "o.blow5"))
     assert nr == 11 and ns == sum(len(v) for v in sigs.values())
     assert a["records"] == b["records"]
+
+
+@pytest.mark.parametrize("kernel_copy", [True, False])
+def test_splice_blow5_parts_equals_single_writer(tmp_path, monkeypatch, kernel_copy):
+    """The parallel end of a sharded run, driven serially here: a fake process group hands every "rank" the gathered
+    (bytes, samples, header) triples; rank 0's part becomes the output, the others splice themselves in (with and
+    without os.copy_file_range).  A rank without reads, a rank whose reads are all empty, skipped (empty) reads inside
+    a shard: record bytes equal to one writer's."""
+    import os
+    from seq2squiggle_b200 import inference as inf
+    from seq2squiggle_b200.profiles import get_profile
+    from seq2squiggle_b200.signal_io import BLOW5Writer
+    if not kernel_copy:
+        monkeypatch.delattr(os, "copy_file_range", raising=False)
+    rng = np.random.default_rng(4)
+    prof = get_profile("dna-r10-prom")
+    sigs = {f"r{i}": rng.integers(-100, 900, size=0 if i in (2, 7, 8) else int(rng.integers(1, 300))).astype(np.int16)
+            for i in range(13)}
+    names = list(sigs)
+    single = BLOW5Writer(str(tmp_path / "single.blow5"), prof, True, "dna-r10-prom", False)
+    single.signals = sigs
+    single.save()
+    shards = ((0, 4), (4, 4), (4, 7), (7, 9), (9, 13))                    # rank 1: no reads; rank 3: only empty reads
+    out = str(tmp_path / "o.blow5")
+    writers = []
+    for r, (lo, hi) in enumerate(shards):
+        w = BLOW5Writer(inf.part_path(out, r), prof, True, "dna-r10-prom", False)
+        w._id_base = lo
+        w.signals = {n: sigs[n] for n in names[lo:hi]}
+        w.save()
+        writers.append(w)
+    info = [(inf.blow5_record_span(w.filename)[1] - inf.blow5_record_span(w.filename)[0], w.samples_written,
+             inf.blow5_record_span(w.filename)[0]) for w in writers]
+
+    class FakeDist:     # the collective calls of one rank; ranks are run in the order the barriers would enforce
+        @staticmethod
+        def all_gather_object(lst, obj):
+            lst[:] = info
+
+        @staticmethod
+        def barrier():
+            pass
+
+    for r, w in enumerate(writers):                                        # rank 0 first (rename + truncate), then the rest
+        inf.splice_parts_collective(out, w.filename, r, len(shards), w.samples_written, FakeDist)
+    with open(out, "r+b") as f:                                            # rank 0's closing step ran before the others' splices here
+        f.seek(-5, 2)
+        f.write(b"5WOLB")
+    blobs = []
+    for path in (str(tmp_path / "single.blow5"), out):
+        lo, hi = inf.blow5_record_span(path)
+        blobs.append(open(path, "rb").read()[lo:])
+    assert blobs[0] == blobs[1]
+    assert not any(os.path.exists(inf.part_path(out, r)) for r in range(len(shards)))

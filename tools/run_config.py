@@ -91,6 +91,8 @@ def main():
                 f.write(g[i:i + 70] + "\n")
     out = a.out or os.path.join(tmp, "sim.blow5")
     inference.get_reads = timed("get_reads (genome preprocessing + read sampling)", reads_mod.get_reads)
+    inference.get_reads_shard = timed("get_reads_shard (genome preprocessing + lengths-only replay)", reads_mod.get_reads_shard)
+    inference.splice_parts_collective = timed("splice_parts_collective (parallel merge of the parts)", inference.splice_parts_collective)
     from seq2squiggle_b200 import model as M
     M.seq2squiggle.predict_reads = timed("predict_reads (pack + enqueue, blocks on the previous batch)", M.seq2squiggle.predict_reads)
     M.seq2squiggle.on_predict_epoch_end = timed("on_predict_epoch_end (drain + writer join)", M.seq2squiggle.on_predict_epoch_end)
