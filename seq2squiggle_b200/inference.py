@@ -243,8 +243,13 @@ def splice_parts_collective(out: str, my_part: str, rank: int, world: int, my_sa
 
 def part_path(out: str, rank: int) -> str:
     """Per-rank part file of a multi-GPU run: ``sim.blow5`` -> ``sim.part<rank>.blow5`` (keeps the extension, so the
-    writer factory's extension check applies to it as to any output)."""
+    writer factory's extension check applies to it as to any output).  ``S2S_PART_DIR`` moves the parts of the ranks
+    > 0 to another directory — a tmpfs such as /dev/shm turns "write the part, then copy it into the output" into one
+    pass over the disk; rank 0's part stays beside ``out`` because it *becomes* the output by a rename."""
     stem, ext = os.path.splitext(str(out))
+    part_dir = os.environ.get("S2S_PART_DIR")
+    if part_dir and rank > 0:
+        stem = os.path.join(part_dir, os.path.basename(stem))
     return f"{stem}.part{rank}{ext}"
 
 

@@ -68,7 +68,10 @@ import pytest
 
 
 @pytest.mark.parametrize("world", [2, 3])
-def test_sharded_run_equals_single_process(tmp_path, world):
+def test_sharded_run_equals_single_process(tmp_path, world, monkeypatch):
+    if world == 3:      # parts of the ranks > 0 in another directory (S2S_PART_DIR, e.g. a tmpfs)
+        (tmp_path / "parts").mkdir()
+        monkeypatch.setenv("S2S_PART_DIR", str(tmp_path / "parts"))
     from tests.blow5_reader import read_blow5
     script = tmp_path / "worker.py"
     script.write_text(WORKER % {"root": ROOT})
@@ -94,3 +97,5 @@ def test_sharded_run_equals_single_process(tmp_path, world):
         assert len(data) == hi + 5
         blobs.append(data[lo:])
     assert blobs[0] == blobs[1]
+    assert sorted(os.listdir(tmp_path)) == sorted(["worker.py", "one.blow5", "many.blow5"] + (["parts"] if world == 3 else []))
+    assert world != 3 or os.listdir(tmp_path / "parts") == []
