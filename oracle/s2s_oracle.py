@@ -11,7 +11,7 @@ reference's own modules (``oracle/make_golden.py``).
 from __future__ import annotations
 
 from collections import OrderedDict, defaultdict
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch

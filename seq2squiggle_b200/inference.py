@@ -20,7 +20,6 @@ from __future__ import annotations
 import logging
 import os
 import struct
-import uuid
 from typing import Iterable, Iterator, List, Sequence, Tuple
 
 import numpy as np

@@ -19,7 +19,7 @@ import logging
 import os
 import uuid
 from datetime import datetime
-from typing import Dict, Optional
+from typing import Optional
 
 import numpy as np
 

@@ -1,6 +1,5 @@
 """GPU tests of the reference-facing plug points (model.seq2squiggle, inference_run, the CLI) — everything goes
 through libs2s_b200.so; the oracle only checks."""
-import json
 import os
 import random
 import subprocess

@@ -4,8 +4,6 @@ the BLOW5 part merge of the multi-GPU path."""
 import ctypes
 import os
 import re
-import subprocess
-import sys
 
 import numpy as np
 import pytest

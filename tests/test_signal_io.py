@@ -1,6 +1,5 @@
 """SLOW5/BLOW5 writer (native libs2s_blow5.so behind seq2squiggle_b200.signal_io) read back with an independent
 parser; record fields as the reference fills them (signal_io.py:104-171)."""
-import os
 
 import numpy as np
 import pytest
