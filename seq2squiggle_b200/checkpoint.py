@@ -22,21 +22,39 @@ ARCH_FIXED = dict(dmodel=64, dff=256, encoder_heads=8, decoder_heads=8, max_dna_
                   pre_layers=1)
 
 
+# Defaults of ``seq2squiggle predict`` when no ``-y`` YAML is given (values of the reference's packaged config.yaml:14-47;
+# a reference YAML passed with ``-y`` and a reference checkpoint's ``hyper_parameters["config"]`` carry the same keys,
+# which is what ``check_model`` walks).  Grouped by who reads them here.
+DEFAULT_CONFIG = {
+    # the geometry of one chunk and the architecture the kernels are compiled for (ARCH_FIXED) / sized by
+    "seq_kmer": 9, "allowed_chars": "_ACGT", "max_dna_len": 16, "max_signal_len": 250, "scaling_max_value": 165.0,
+    "pre_layers": 1, "dmodel": 64, "dff": 256,
+    "encoder_layers": 2, "encoder_heads": 8, "decoder_layers": 2, "decoder_heads": 8,
+    # inert at predict time (eval mode) but compared by check_model
+    "encoder_dropout": 0.2, "decoder_dropout": 0.2, "duration_dropout": 0.2,
+    # training / preprocessing / logging keys: never read on the predict path, carried so that a checkpoint written from
+    # this config and the reference's own compare key by key (mismatches only log a warning, inference.py:224-267)
+    "log_name": "Human-R1041-4khz", "wandb_logger_state": "disabled",
+    "max_chunks_train": 210000000, "max_chunks_valid": 100000, "train_valid_split": 0.9,
+    "train_batch_size": 512, "max_epochs": 25, "save_model": True, "optimizer": "Adam", "warmup_ratio": 0.01,
+    "lr": 0.0005, "weight_decay": 0.0, "lr_schedule": "warmup_cosine", "gradient_clip_val": 1.0,
+}
+
+
 def set_config(config_path=None) -> dict:
-    """seq2squiggle.py:640-657: the default YAML lives inside the package."""
-    default = os.path.join(os.path.dirname(__file__), "config.yaml")
-    path = default if config_path is None else config_path
-    try:
-        with open(path, "r") as fh:
-            config = yaml.safe_load(fh)
-    except FileNotFoundError:
-        logger.error(f"Configuration file not found: {path}")
-        raise
-    except yaml.YAMLError as exc:
-        logger.error(f"Error parsing YAML file: {path} - {exc}")
-        raise
+    """seq2squiggle.py:640-657: a YAML given with ``-y``, else the packaged defaults."""
     if config_path is None:
         logger.info("Config file was not specified. Default config will be used.")
+        return dict(DEFAULT_CONFIG)
+    try:
+        with open(config_path, "r") as fh:
+            config = yaml.safe_load(fh)
+    except FileNotFoundError:
+        logger.error(f"Configuration file not found: {config_path}")
+        raise
+    except yaml.YAMLError as exc:
+        logger.error(f"Error parsing YAML file: {config_path} - {exc}")
+        raise
     return config
 
 

@@ -241,3 +241,21 @@ def test_splice_blow5_parts_equals_single_writer(tmp_path, monkeypatch, kernel_c
         blobs.append(open(path, "rb").read()[lo:])
     assert blobs[0] == blobs[1]
     assert not any(os.path.exists(inf.part_path(out, r)) for r in range(len(shards)))
+
+
+def test_default_config_equals_reference_yaml():
+    """The packaged defaults (checkpoint.DEFAULT_CONFIG) carry the reference's config.yaml key for key, value for value,
+    type for type (checked against the reference tree when it is mounted, against the golden checkpoint's stored config
+    otherwise: oracle/make_golden.py wrote it from the reference YAML)."""
+    import yaml
+    import torch
+    from seq2squiggle_b200.checkpoint import DEFAULT_CONFIG, set_config
+    assert set_config(None) == DEFAULT_CONFIG and set_config(None) is not DEFAULT_CONFIG
+    ref_yaml = "/root/reference/src/seq2squiggle/config.yaml"
+    if os.path.exists(ref_yaml):
+        ref = yaml.safe_load(open(ref_yaml))
+    else:
+        ck = torch.load(os.path.join(ROOT, "tests", "golden", "ckpt_k9_seed1.ckpt"), map_location="cpu", weights_only=False)
+        ref = ck["hyper_parameters"]["config"]
+    assert DEFAULT_CONFIG == ref
+    assert all(type(DEFAULT_CONFIG[k]) is type(ref[k]) for k in ref)
