@@ -16,10 +16,12 @@ module-level generator is seeded once by ``set_seeds`` (``utils.py:722-741``).
 from __future__ import annotations
 
 import gzip
+import itertools
 import logging
 import os
 import random
 import re
+from bisect import bisect_right
 from typing import Generator, Iterable, List, Sequence, Tuple
 from uuid import uuid4
 
@@ -243,6 +245,7 @@ def sampling_iter(num_seqs, genome_seqs, genome_lens, r, seed, total_len, distr,
     vectorised = distr == "expon" and r > 0 and num_seqs > 0 and 0 <= seed and seed + num_seqs * (max_retries + 1) < 2 ** 32
     first_len, block0, kBlock = None, 0, 8192
     has_n = ["N" in g for g in genome_seqs]
+    cum_lens = list(itertools.accumulate(genome_lens))
     debug = logger.isEnabledFor(logging.DEBUG)
     accepted = 0
     randint, choice = random.randint, random.choice
@@ -252,10 +255,10 @@ def sampling_iter(num_seqs, genome_seqs, genome_lens, r, seed, total_len, distr,
         retries = 0
         while retries < max_retries:
             start_pos = randint(0, total_genome_len - 1)
-            if len(genome_lens) == 1:
-                genome_index, start_index = 0, start_pos
-            else:
-                genome_index, start_index = get_genome_and_position(genome_lens, start_pos)
+            # get_genome_and_position (utils.py:359-371) by bisection: a transcriptome has 10^5 sequences, and the
+            # reference's linear walk (plus a sum over all lengths) per read is what dominates there
+            genome_index = bisect_right(cum_lens, start_pos)
+            start_index = start_pos - (cum_lens[genome_index - 1] if genome_index else 0)
             genome = genome_seqs[genome_index]
             if vectorised and retries == 0:
                 if first_len is None or read_i >= block0 + kBlock:

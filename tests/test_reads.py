@@ -139,6 +139,20 @@ def test_sharded_sampling_equals_eager(tmp_path):
     assert parts == full
 
 
+def test_contig_lookup_by_bisection_equals_reference_walk():
+    """sampling_iter finds (contig, offset) of a genome-wide position by bisection; utils.py:359-371 walks the contigs.
+    Same answer for every position, including contigs of length 0 and the last base."""
+    import itertools
+    from bisect import bisect_right
+    lens = [5, 0, 1, 7, 0, 0, 3]
+    cum = list(itertools.accumulate(lens))
+    for pos in range(sum(lens)):
+        gi = bisect_right(cum, pos)
+        assert (gi, pos - (cum[gi - 1] if gi else 0)) == R.get_genome_and_position(lens, pos)
+    with pytest.raises(ValueError):
+        R.get_genome_and_position(lens, sum(lens))
+
+
 def test_fasta_fastq_parser(tmp_path):
     fa = tmp_path / "a.fasta"
     fa.write_text(">r1 desc here\nACGT\nacgtNN\n\n>r2\nTTTT\n>empty\n>r3\tx\nGG\r\nCC\r\n")
