@@ -3,8 +3,11 @@
 
   python profiles/ncu_summary.py launches gpurun_out/X_launches.csv          > profiles/rNN_launches.txt
   python profiles/ncu_summary.py kernel   gpurun_out/X.ncu-rep [launch_idx]  > profiles/rNN_<kernel>_ncu.txt
+  python profiles/ncu_summary.py hotspots gpurun_out/X.ncu-rep [launch_idx]  > profiles/rNN_<kernel>_source_hotspots.txt
 
 `launches` aggregates the `--metrics gpu__time_duration.sum` launch list per kernel (count, total, share).
+`hotspots` walks the SASS program of one profiled launch in segments of 100 instructions and prints where the warp-stall
+samples sit (segment share + its three hottest instructions), then the hottest instruction with what precedes it.
 `kernel` prints the metrics of one profiled launch of an `ncu --set full` report that the roofline discussion in
 DESIGN.md uses: duration, DRAM bytes, pipe utilisation, issue/stall breakdown, occupancy limits, and the
 per-opcode warp-stall samples from the source page (needs -lineinfo / --import-source on).
@@ -84,8 +87,39 @@ def kernel(path, idx=0):
     print("# Blackwell-native opcodes present:", ", ".join(f"{op} x{execd[op]}" for op in sorted(mn)))
 
 
+def hotspots(path, idx=0, seg=100, floor=0.015):
+    src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass"],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(src.splitlines()))
+    starts = [i for i, x in enumerate(rows) if x and x[0] == "Kernel Name"]
+    s = starts[min(idx, len(starts) - 1)]
+    e = starts[starts.index(s) + 1] if starts.index(s) + 1 < len(starts) else len(rows)
+    hdr, body = rows[s + 1], [x for x in rows[s + 2:e] if len(x) > 4]
+    si, ci = hdr.index("# Samples"), hdr.index("Source")
+    n = [int(x[si]) for x in body]
+    tot = sum(n) or 1
+    print(f"# {path}, launch {idx} ({rows[s][1][:60]}...): warp-stall samples along the SASS program")
+    print(f"# {len(body)} instructions, {tot} samples; segments of {seg} instructions with >= {100 * floor:.1f} % of the "
+          f"samples, top three instructions of each")
+    for a in range(0, len(body), seg):
+        share = sum(n[a:a + seg]) / tot
+        if share < floor:
+            continue
+        top = sorted(range(a, min(a + seg, len(body))), key=lambda i: -n[i])[:3]
+        print(f"[{a:5d}-{a + seg:5d}] {100 * share:5.1f}%  " +
+              " | ".join(f"{body[i][ci].strip()[:44]} ({100 * n[i] / tot:.1f}%)" for i in top))
+    spins = ("BRA", "SYNCS", "BAR", "NOP", "ISETP", "BSYNC", "FENCE")      # barrier / mbarrier wait loops
+    cand = [i for i in range(len(body)) if not any(t in body[i][ci] for t in spins)]
+    hot = max(cand, key=lambda i: n[i])
+    print(f"\n# the hottest non-wait instruction ({100 * n[hot] / tot:.1f} % of the samples) and what precedes it")
+    for i in range(max(hot - 12, 0), min(hot + 3, len(body))):
+        print(f"{i:5d} {n[i]:>6d}  {body[i][ci].strip()[:80]}")
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "hotspots":
+        hotspots(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 0)
     else:
         kernel(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 0)
