@@ -259,3 +259,39 @@ def test_default_config_equals_reference_yaml():
         ref = ck["hyper_parameters"]["config"]
     assert DEFAULT_CONFIG == ref
     assert all(type(DEFAULT_CONFIG[k]) is type(ref[k]) for k in ref)
+
+
+def test_shipped_library_is_blackwell_native():
+    """Static check of the built library (cuobjdump -sass, no GPU needed): the decoder attention and the fc + FFN kernels
+    issue tcgen05.mma (UTCHMMA), read / write TMEM (LDTM / STTM), load by TMA (UTMALDG) and synchronise on mbarriers
+    (SYNCS); the FFN block output leaves by a TMA store (UTMASTG); no legacy mma.sync (HMMA) exists anywhere."""
+    import re
+    import shutil
+    import subprocess
+    from collections import Counter
+    from seq2squiggle_b200 import _lib
+    if shutil.which("cuobjdump") is None or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not available")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    per_kernel, cur = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = per_kernel.setdefault(m.group(1), Counter())
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\w+\s+)?([A-Z][A-Z0-9_]*)", line)
+        if m and cur is not None:
+            cur[m.group(1)] += 1
+    assert sum(c["HMMA"] for c in per_kernel.values()) == 0
+
+    def kernels(tag):
+        found = [c for name, c in per_kernel.items() if tag in name]
+        assert found, f"no kernel named *{tag}* in the library"
+        return found
+
+    for tag in ("k_tc_attn2", "k_tc_fc_ffn", "k_tc_qkv_plain"):
+        for c in kernels(tag):
+            assert c["UTCHMMA"] > 0 and c["LDTM"] > 0 and c["UTMALDG"] > 0 and c["SYNCS"] > 0, (tag, dict(c))
+    assert all(c["STTM"] > 0 for c in kernels("k_tc_attn2") + kernels("k_tc_fc_ffn"))   # fp16 P / hidden written back to TMEM
+    assert any(c["UTMASTG"] > 0 for c in kernels("k_tc_fc_ffn"))
+    assert all(c["MUFU"] > 0 for c in kernels("k_tc_attn2"))
