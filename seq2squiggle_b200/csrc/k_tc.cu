@@ -30,7 +30,7 @@ constexpr uint32_t kWaitLimit = 1u << 22;
 constexpr int kSlab = 128 * 128;  // bytes of one [128 rows x 128 B] tile
 
 // status codes written on a barrier timeout
-enum { kErrQkvLoad = 11, kErrQkvMma = 12, kErrAttLoad = 21, kErrAttS = 22, kErrAttO = 23, kErrFcLoad = 31,
+enum { kErrQkvLoad = 11, kErrQkvMma = 12, kErrAttLoad = 21, kErrAttS = 22, kErrAttO = 23, kErrAttTmem = 24, kErrFcLoad = 31,
        kErrFcMma = 32, kErrFfnLoad = 41, kErrFfnMma1 = 42, kErrFfnMma2 = 43 };
 
 // Optional phase timing of k_tc_attn (compile with -DS2S_PHASE_TIMING): clock64() deltas of thread 0 of every CTA,
@@ -444,6 +444,7 @@ __global__ void k_attn_gate(const int* __restrict__ hint, int probe, int n_units
   }
 }
 #include "k_tc_attn4.cuh"
+#include "k_tc_attn3.cuh"
 
 // =================================================================================================
 // FFN: X' = LN2(relu(Y W1^T + b1) W2^T + b2 + Y) with Y = LN1(O Wfc^T + b + X), one kernel, 128 rows per
@@ -825,6 +826,7 @@ int tc_init(TcState& s, const DevWeights& w, int device) {
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn4, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt));
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn3, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt3));
   if (const char* env = getenv("S2S_ATTN_V1")) s.attn_v1 = atoi(env) != 0;
   if (const char* env = getenv("S2S_ATTN_V2")) s.attn_v1 = atoi(env) == 0;
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
@@ -887,7 +889,7 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* p_out
       // S2S_ATTN_VER=4 selects k_tc_attn4 (16 softmax warps per SM): parity-green but measured SLOWER than k_tc_attn2
       // (2.96 vs 2.40 ms per 16384 chunks): with 4-5 busy warps per scheduler the MMA issue warps get too few issue slots
       // and the softmax warps wait for S (profiles/r01_attn4_experiment.txt).
-      static const int attn_ver = getenv("S2S_ATTN_VER") ? atoi(getenv("S2S_ATTN_VER")) : 2;
+      static const int attn_ver = getenv("S2S_ATTN_VER") ? atoi(getenv("S2S_ATTN_VER")) : 3;
       // S2S_ATTN_BOUND=1: Cauchy-Schwarz reference folded into the S MMA (k_tc_attn2<true>): parity-green, no scaling FFMA
       // and no row-max pass, but measured no faster (4.76 vs 4.76-4.92 ms per 32768 chunks): the exp pass is bound by the
       // XU pipe, which also executes the F2FP packs (8 (1 - f) + 1 clk per exponential per scheduler).
@@ -896,7 +898,13 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* p_out
       int* hint = s.d_status + 8 + l;
       if (attn_ver != 4)
         k_attn_gate<<<64, 256, 0, st>>>(hint, s.attn_calls % 16 == 15, n_units, d_flags + 1, d_flags, s.d_status);
-      if (attn_ver != 4 && attn_bound)
+      if (attn_ver == 3) {
+        // one 512-thread CTA per SM; an even grid keeps every CTA on one head group
+        int grid3 = s.sm_count & ~1;
+        if (grid3 > n_units) grid3 = n_units;
+        k_tc_attn3<<<grid3, kAttn3Threads, kSmemAtt3, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags,
+                                                             s.d_status);
+      } else if (attn_ver != 4 && attn_bound)
         k_tc_attn2<true><<<grid2a, kAttn2Threads, smem2a, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags,
                                                                    s.d_status);
       else if (attn_ver != 4)

@@ -17,6 +17,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "../../seq2squiggle_b200/csrc/tc_prims.cuh"
 
@@ -182,12 +183,14 @@ __device__ __forceinline__ uint32_t poly_h2_lea(float x0, float x1) {
 }
 
 // kPoly pairs of 16 by the polynomial; kPrmt: MUFU pairs packed as bf16 by PRMT; kLea: polynomial with the integer 2^n
-template <int kPoly, bool kPrmt, bool kLea>
+// kDirect: the accumulator already holds the exponent (reference folded into the S MMA): no scaling FFMA per score
+template <int kPoly, bool kPrmt, bool kLea, bool kDirect = false>
 __device__ __forceinline__ void exp_step(const uint32_t (&r)[32], uint32_t taddr) {
   uint32_t pk[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const float x0 = fmaf(__uint_as_float(r[2 * i]), 0.5f, -1.f), x1 = fmaf(__uint_as_float(r[2 * i + 1]), 0.5f, -1.f);
+    const float x0 = kDirect ? __uint_as_float(r[2 * i]) : fmaf(__uint_as_float(r[2 * i]), 0.5f, -1.f);
+    const float x1 = kDirect ? __uint_as_float(r[2 * i + 1]) : fmaf(__uint_as_float(r[2 * i + 1]), 0.5f, -1.f);
     if ((i * kPoly) % 16 < kPoly) {
       pk[i] = kLea ? poly_h2_lea(x0, x1) : poly_h2_shipped(x0, x1);
     } else {
@@ -198,7 +201,7 @@ __device__ __forceinline__ void exp_step(const uint32_t (&r)[32], uint32_t taddr
   tmem_st_32x16(taddr, pk);
 }
 
-template <int kPoly, bool kPrmt, bool kLea>
+template <int kPoly, bool kPrmt, bool kLea, bool kDirect = false>
 __global__ void __launch_bounds__(512) k_exp(int reps, long long* out, float* sink) {
   __shared__ uint32_t s_base;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -216,9 +219,9 @@ __global__ void __launch_bounds__(512) k_exp(int reps, long long* out, float* si
     for (int c = 0; c < 8; c += 2) {
       tmem_ld_32x32(lane_addr + ((c + 1) & 3) * 32, rb);
       tmem_wait_ld();
-      exp_step<kPoly, kPrmt, kLea>(ra, lane_addr + (c & 3) * 16);
+      exp_step<kPoly, kPrmt, kLea, kDirect>(ra, lane_addr + (c & 3) * 16);
       if (c + 2 < 8) tmem_ld_32x32(lane_addr + ((c + 2) & 3) * 32, ra);
-      exp_step<kPoly, kPrmt, kLea>(rb, lane_addr + ((c + 1) & 3) * 16);
+      exp_step<kPoly, kPrmt, kLea, kDirect>(rb, lane_addr + ((c + 1) & 3) * 16);
     }
     tmem_wait_st();
   }
@@ -230,17 +233,17 @@ __global__ void __launch_bounds__(512) k_exp(int reps, long long* out, float* si
   if (warp == 0) tmem_dealloc<512>(s_base);
 }
 
-template <int kPoly, bool kPrmt, bool kLea>
+template <int kPoly, bool kPrmt, bool kLea, bool kDirect = false>
 void run_exp(long long* out, float* sink) {
   long long h[16];
-  for (int threads : {128, 256}) {
+  for (int threads : {128, 256, 384}) {
     const int reps = 200;
-    k_exp<kPoly, kPrmt, kLea><<<1, threads>>>(reps, out, sink);
+    k_exp<kPoly, kPrmt, kLea, kDirect><<<1, threads>>>(reps, out, sink);
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(h, out, sizeof h, cudaMemcpyDeviceToHost);
     const double per = (double)h[0] / (reps * 8);
-    printf("exp pass, %2d/16 polynomial pairs, MUFU pack by %s, 2^n by %s, %d warps/scheduler: %6.1f clk per 32-column step "
-           "per warp -> %5.2f clk per exp row per scheduler [%s]\n", kPoly, kPrmt ? "PRMT (bf16)" : "F2FP (fp16)",
+    printf("exp pass%s, %2d/16 polynomial pairs, MUFU pack by %s, 2^n by %s, %d warps/scheduler: %6.1f clk per 32-column step "
+           "per warp -> %5.2f clk per exp row per scheduler [%s]\n", kDirect ? " (direct, no FFMA)" : "", kPoly, kPrmt ? "PRMT (bf16)" : "F2FP (fp16)",
            kLea ? "LEA + const  " : "shift/mask/HMUL2", threads / 128, per, per / 32 / (threads / 128), cudaGetErrorString(e));
   }
 }
@@ -262,7 +265,9 @@ __global__ void k_poly_check(float* worst) {
   atomicMax(reinterpret_cast<int*>(worst + 1), __float_as_int(e_abs));
 }
 
-int main() {
+int main(int argc, char** argv) {
+  // every part in its own process: an illegal-instruction fault (part A2 on B200) is sticky for the whole context
+  const char* part = argc > 1 ? argv[1] : "B";
   long long* out;
   float *sink, *d_dev;
   int* status;
@@ -271,9 +276,9 @@ int main() {
   cudaMalloc(&d_dev, 128 * 16 * sizeof(float));
   cudaMalloc(&status, 4);
   cudaFuncSetAttribute(k_mixed_fmt, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 1024);
-  run_mixed("A fp16 / B fp16", kFmtF16, kFmtF16, d_dev, status);
-  run_mixed("A bf16 / B fp16 (?)", kFmtBF16, kFmtF16, d_dev, status);
-  run_mixed("A bf16 / B bf16", kFmtBF16, kFmtBF16, d_dev, status);
+  if (!strcmp(part, "A1")) { run_mixed("A fp16 / B fp16", kFmtF16, kFmtF16, d_dev, status); return 0; }
+  if (!strcmp(part, "A2")) { run_mixed("A bf16 / B fp16 (?)", kFmtBF16, kFmtF16, d_dev, status); return 0; }
+  if (!strcmp(part, "A3")) { run_mixed("A bf16 / B bf16", kFmtBF16, kFmtBF16, d_dev, status); return 0; }
 
   float* worst;
   cudaMalloc(&worst, 8);
@@ -289,5 +294,12 @@ int main() {
   run_exp<5, false, true>(out, sink);  run_exp<5, true, true>(out, sink);
   run_exp<8, false, false>(out, sink); run_exp<8, true, false>(out, sink);
   run_exp<8, false, true>(out, sink);  run_exp<8, true, true>(out, sink);
+  // round 2: exponent straight from the accumulator (k_tc_attn3: reference folded into the S MMA)
+  run_exp<0, false, false, true>(out, sink);
+  run_exp<6, false, false, true>(out, sink); run_exp<7, false, false, true>(out, sink);
+  run_exp<8, false, false, true>(out, sink); run_exp<9, false, false, true>(out, sink);
+  run_exp<10, false, false, true>(out, sink); run_exp<11, false, false, true>(out, sink);
+  run_exp<8, false, true, true>(out, sink); run_exp<9, false, true, true>(out, sink); run_exp<10, false, true, true>(out, sink);
+  run_exp<8, true, false, true>(out, sink); run_exp<10, true, true, true>(out, sink);
   return 0;
 }
