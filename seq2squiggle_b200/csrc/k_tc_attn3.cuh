@@ -1,16 +1,18 @@
 // k_tc_attn3 — warp-specialised decoder attention (included by k_tc.cu inside namespace s2s::{anonymous}).
 //
-// layers.py:19-41, 64-88 for one (chunk, group of 4 heads) per "unit", ONE 512-thread CTA per SM, whole TMEM (512 columns).
+// layers.py:19-41, 64-88 for one (chunk, group of 4 heads) per "unit", ONE 864-thread CTA per SM, whole TMEM (512 columns).
 // The d_k = 8 attention is bound by the softmax exponentials, so everything else is moved off the softmax warps and the
 // exponent arrives in TMEM ready to use:
-//   warps 0-3 / 4-7   softmax warpgroups (query tile 0 / 1 of the chunk, one query row per thread): per 64-key quarter
-//                     tcgen05.ld -> 2^x (MUFU.EX2 or packed-fp16 polynomial) -> fp16 P over S in TMEM, nothing else;
-//   warps 8-11        producer warpgroup: QKV-projection epilogue of the NEXT unit (accumulator -> fp16 Q / K / V^T in the
+//   warps 0-15        four softmax warpgroups = (query tile 0 / 1 of the chunk) x (half of every 64-key quarter), one query
+//                     row per thread: tcgen05.ld 32 scores -> 2^x (MUFU.EX2 or packed-fp16 polynomial) -> fp16 P over S in
+//                     TMEM, nothing else; four of them per scheduler cover each other's barrier and TMEM round trips;
+//   warps 16-19       producer warpgroup: QKV-projection epilogue of the NEXT unit (accumulator -> fp16 Q / K / V^T in the
 //                     UMMA operand layouts, double-buffered in shared memory) while the softmax warps work on this one;
-//   warps 12 / 13     MMA issue warps, one per softmax warpgroup: S quarters (SS, N=64) and P.V steps (TS, N=16) from a
+//   warps 20-23       output warpgroup: O accumulator -> normalise by the denominator -> + V bias -> fp16 rows in HBM;
+//   warps 24 / 25     MMA issue warps, one per query tile: S quarters (SS, N=64) and P.V steps (TS, N=16) from a
 //                     fully unrolled 16-quarter schedule, every descriptor a compile-time offset from a uniform base
 //                     (an MMA whose operands are computed at run time costs 116-130 clk of issue, profiles/r01_mma_rate.txt);
-//   warp 14           TMA loads of the X tiles / weight block and the QKV-projection MMAs;   warp 15 idle.
+//   warp 26           TMA loads of the X tiles / weight block and the QKV-projection MMAs.
 // The softmax reference is folded into the S MMA: every head owns a K=16 operand slice,
 //   A_i = [ c q_i (8) | -m_i, -30000, 0 x 6 ],  B_j = [ k_j (8) | 1, pad_j, 0 x 6 ],   c = log2(e)/sqrt(d_k),
 // so the accumulator holds x_ij = c q_i.k_j - m_i (and about -30000 for the six pad keys 250..255, whose P is exactly 0)
@@ -20,13 +22,13 @@
 // (11 nats): then the fp16 P overflows, the row's denominator (accumulated by the tensor core from the same rounded P
 // through a ones row of V^T) is inf/NaN, and the unit is flagged and recomputed by the exact two-pass kernel k_tc_attn.
 // K bias is dropped (adds a per-row constant to the scores) and the V bias is added to the normalised output.
-// TMEM columns: warpgroup g: ring of three 64-column S/P buffers at 208 g + {0, 64, 128}, O accumulator at 208 g + 192
+// TMEM columns: query tile g: ring of three 64-column S/P buffers at 208 g + {0, 64, 128}, O accumulator at 208 g + 192
 // (16 columns: 8 values, the denominator, 7 unused); QKV accumulator (one 128-row tile, 96 columns) at 416.
 // Barriers complete once per use; both sides derive the parity from the same use counts (the ring restarts at slot 0
 // every unit; slot 0 is used 6 times per unit, slots 1 and 2 five times).
 #pragma once
 
-constexpr int kAttn3Threads = 512;
+constexpr int kAttn3Threads = 864;   // 27 warps, 72 registers per thread; no setmaxnreg (the pool of a CTA is what it was launched with)
 #ifndef S2S_POLY3_H2
 #define S2S_POLY3_H2 8
 #endif
@@ -62,7 +64,7 @@ __device__ __forceinline__ void exp32_store(const uint32_t (&r)[32], uint32_t ta
 #endif
 
 struct A3Bars {  // indices into the barrier array
-  enum { W = 0, X = 1, QKV = 3, ACC = 4, KV = 5, DONE = 7, S = 9, P = 15, PV = 21, OF = 27, COUNT = 29 };
+  enum { W = 0, X = 1, QKV = 3, ACC = 4, KV = 5, DONE = 7, S = 9, P = 15, PV = 21, OF = 27, OR = 29, COUNT = 31 };
 };
 
 __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_constant__ CUtensorMap tmX,
@@ -90,12 +92,13 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bars[A3Bars::X + b], 1);
       mbar_init(&bars[A3Bars::KV + b], 4);
-      mbar_init(&bars[A3Bars::DONE + b], 8);
+      mbar_init(&bars[A3Bars::DONE + b], 4);
       mbar_init(&bars[A3Bars::OF + b], 4);
+      mbar_init(&bars[A3Bars::OR + b], 1);
     }
     for (int i = 0; i < 6; ++i) {
       mbar_init(&bars[A3Bars::S + i], 1);
-      mbar_init(&bars[A3Bars::P + i], 4);
+      mbar_init(&bars[A3Bars::P + i], 8);
       mbar_init(&bars[A3Bars::PV + i], 1);
     }
     fence_mbar_init();
@@ -152,110 +155,47 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
   const int n_it = (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // units of this CTA
   const int g = blockIdx.x & 1;   // even grid stride: a CTA keeps its head group
 
-  if (warp < 8) {
+  if (warp < 16) {
     // =============================== softmax warpgroups ===========================================
-    const int wg = warp >> 2;
-    const uint32_t lane_addr = tmem_addr(0u, (warp & 3) * 32, 208 * wg);
-    const int r = (warp & 3) * 32 + lane;   // query row inside the tile
+    // Four warpgroups: (query tile, half of every 64-key quarter).  Both halves of a tile work on the same ring slot: half
+    // h loads S columns [32 h, 32 h + 32) and writes its 16 packed P columns at [32 h, 32 h + 16) of the slot (inside its
+    // own S columns, so it cannot overwrite scores the other half has not loaded yet).  Four softmax warps per scheduler
+    // cover each other's barrier / TMEM round trips; the barrier of the next quarter is probed before this quarter's
+    // exponentials so that its ~100 clk round trip is hidden too.
+    const int wg = warp >> 3, half = (warp >> 2) & 1;
+    const uint32_t lane_addr = tmem_addr(0u, (warp & 3) * 32, 208 * wg + 32 * half);
+    const uint32_t barS = BAR(A3Bars::S + 3 * wg), barP = BAR(A3Bars::P + 3 * wg);
     uint32_t bits = 0;                       // parity bits of the ring slots (bit s = parity of the slot's next use)
     A3PH_DECL
     for (int it = 0; it < n_it; ++it) {
       if (lds_u32(abort_a)) break;
-      const int unit = blockIdx.x + it * gridDim.x;
-      const int chunk = unit >> 1;
-      bool overflow = false;
       uint32_t slot = 0;
-      auto ring_next = [&](uint32_t& ob, uint32_t& opar) {
-        ob = slot;
-        opar = (bits >> slot) & 1u;
+      A3PH(5);
+      bool ready = mbar_try_wait_a(barS, bits & 1u);
+#pragma unroll 1
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t cb = slot, cpar = (bits >> slot) & 1u;
         bits ^= 1u << slot;
         slot = (slot == 2u) ? 0u : slot + 1u;
-      };
-      uint32_t ob = 0, opar = 0;   // ring slot of the pending head's last quarter: its PV barrier is "O ready"
-      uint32_t o[16];
-      auto take_O_issue = [&]() {
-        wait_a(BAR(A3Bars::PV + 3 * wg + ob), opar, kErrAttO);
+        if (!ready) wait_a(barS + 8u * cb, cpar, kErrAttS);
+        A3PH(0);
         tcgen05_fence_after();
-        tmem_ld_32x16(lane_addr + 192, o);
-      };
-      auto take_O_finish = [&](int hh) {   // after a tcgen05.wait::ld has covered the load of o[]
+        uint32_t ra[32];
+        tmem_ld_32x32(lane_addr + 64 * cb, ra);
+        // probe the next quarter's barrier now; the answer is only looked at after the exponentials
+        ready = (j < 15) ? mbar_try_wait_a(barS + 8u * slot, (bits >> slot) & 1u) : false;
+        tmem_wait_ld();
+        A3PH(1);
+        exp32_store<kPoly3H2>(ra, lane_addr + 64 * cb);
+        A3PH(2);
+        tmem_wait_st();
         tcgen05_fence_before();
-        warp_arrive_a(BAR(A3Bars::OF + wg));
-        const float den = __uint_as_float(o[8]);   // sum of the rounded probabilities; P_ii = 1, so den >= 1
-        overflow |= !(den < 1e30f) || !(den > 0.25f);
-        const float inv = 1.0f / den;
-        const float* bv = s_bias[g] + 64 + 8 * hh;
-        const int64_t row = (int64_t)chunk * 256 + wg * 128 + r;
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = fmaf(__uint_as_float(o[i]), inv, bv[i]);
-        *reinterpret_cast<uint4*>(o16 + row * 64 + (g * 4 + hh) * 8) =
-            make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
-      };
-      uint32_t cb, cpar;
-      ring_next(cb, cpar);
-      A3PH(5);
-      wait_a(BAR(A3Bars::S + 3 * wg + cb), cpar, kErrAttS);
-      A3PH(0);
-      tcgen05_fence_after();
-      uint32_t ra[32], rb[32];
-      tmem_ld_32x32(lane_addr + 64 * cb, ra);
-      tmem_ld_32x32(lane_addr + 64 * cb + 32, rb);
-#pragma unroll 1
-      for (int hh = 0; hh < 4; ++hh) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const bool has_next = !(hh == 3 && q == 3);
-          uint32_t nb = 0, npar = 0;
-          if (has_next) ring_next(nb, npar);
-          const uint32_t col = lane_addr + 64 * cb, ncol = lane_addr + 64 * nb;
-          tmem_wait_ld();
-          A3PH(1);
-          if (q == 1 && hh > 0) take_O_finish(hh - 1);   // its tcgen05.ld was issued in the middle of the previous quarter
-          A3PH(3);
-          exp32_store<kPoly3H2>(ra, col);
-          A3PH(2);
-          if (q == 0 && hh > 0) take_O_issue();          // O of the previous head: its last P.V was issued a quarter ago
-          A3PH(3);
-          bool ready = false;
-          if (has_next) {
-            ready = __all_sync(0xffffffffu, mbar_test_wait_a(BAR(A3Bars::S + 3 * wg + nb), npar));
-            if (ready) {
-              tcgen05_fence_after();
-              tmem_ld_32x32(ncol, ra);
-            }
-          }
-          exp32_store<kPoly3H2>(rb, col + 16);
-          A3PH(2);
-          if (has_next) {
-            if (!ready) {
-              wait_a(BAR(A3Bars::S + 3 * wg + nb), npar, kErrAttS);
-              tcgen05_fence_after();
-              tmem_ld_32x32(ncol, ra);
-            }
-            tmem_ld_32x32(ncol + 32, rb);
-          }
-          A3PH(0);
-          tmem_wait_st();
-          tcgen05_fence_before();
-          warp_arrive_a(BAR(A3Bars::P + 3 * wg + cb));
-          A3PH(4);
-          if (q == 3) { ob = cb; opar = cpar; }
-          cb = nb; cpar = npar;
-        }
+        warp_arrive_a(barP + 8u * cb);
+        A3PH(4);
       }
-      take_O_issue();
-      tmem_wait_ld();
-      take_O_finish(3);
-      if (__any_sync(0xffffffffu, overflow) && lane == 0) {
-        unit_flags[unit] = 1;
-        atomicAdd(n_flagged, 1);
-      }
-      warp_arrive_a(BAR(A3Bars::DONE + (it & 1)));
-      A3PH(3);
     }
     if (warp == 0) A3PH_FLUSH(0, 6);
-  } else if (warp < 12) {
+  } else if (warp < 20) {
     // =============================== producer warpgroup ===========================================
     const int lq = warp & 3, r = lq * 32 + lane;
     const uint32_t lane_addr = tmem_addr(0u, lq * 32, kA3QkvCol);
@@ -272,13 +212,10 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
         wait_a(BAR(A3Bars::QKV), n & 1u, kErrAttS);
         A3PH(0);
         tcgen05_fence_after();
-        uint32_t rq[32], rk[32], rv[32];
+        uint32_t rq[32], rk[32];
         tmem_ld_32x32(lane_addr, rq);
         tmem_ld_32x32(lane_addr + 32, rk);
-        tmem_ld_32x32(lane_addr + 64, rv);
         tmem_wait_ld();
-        tcgen05_fence_before();
-        warp_arrive_a(BAR(A3Bars::ACC));   // the accumulator may be overwritten by the next tile's projection
         const int t = tile * 128 + r;      // key index inside the chunk
         uint8_t* qrow = ub + tile * kSlab;
         uint8_t* krow = ub + 2 * kSlab;
@@ -300,6 +237,11 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
           *reinterpret_cast<uint4*>(qrow + sw128_offset(r, 2 * hh + 1)) = make_uint4(pack_half2(-m, -30000.0f), 0u, 0u, 0u);
           *reinterpret_cast<uint4*>(krow + sw128_offset(t, 2 * hh)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
+        uint32_t rv[32];   // V after Q / K: 64 + 32 live accumulator registers instead of 96
+        tmem_ld_32x32(lane_addr + 64, rv);
+        tmem_wait_ld();
+        tcgen05_fence_before();
+        warp_arrive_a(BAR(A3Bars::ACC));   // the accumulator may be overwritten by the next tile's projection
         uint8_t* vslab = ub + 4 * kSlab + (t >> 6) * 8192 + (t & 7) * 2;
         const uint32_t ck = (t & 63) >> 3;
 #pragma unroll
@@ -312,11 +254,57 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
       warp_arrive_a(BAR(A3Bars::KV + (it & 1)));
     }
     A3PH(1);
-    if (warp == 8) A3PH_FLUSH(14, 2);
+    if (warp == 16) A3PH_FLUSH(14, 2);
+  } else if (warp < 24) {
+    // =============================== output warpgroup =============================================
+    // O of every (head, query tile): wait for the head's last P.V, read the accumulator, release it to the MMA warp,
+    // normalise by the denominator (column 8), add the V bias, store 16 bytes per row.  Kept off the softmax warps: they
+    // run in lockstep per quarter, so anything one of them does besides exponentials is paid by the whole tile.
+    const int lq = warp & 3, r = lq * 32 + lane;
+    A3PH_DECL
+    for (int it = 0; it < n_it; ++it) {
+      if (lds_u32(abort_a)) break;
+      const int unit = blockIdx.x + it * gridDim.x;
+      const int chunk = unit >> 1;
+      bool overflow = false;
+#pragma unroll 1
+      for (int hh = 0; hh < 4; ++hh) {
+        const float* bv = s_bias[g] + 64 + 8 * hh;
+#pragma unroll 1
+        for (int wg = 0; wg < 2; ++wg) {
+          A3PH(1);
+          wait_a(BAR(A3Bars::OR + wg), (uint32_t)hh & 1u, kErrAttO);   // 4 completions per unit: parity = hh & 1
+          A3PH(0);
+          tcgen05_fence_after();
+          uint32_t o[16];
+          tmem_ld_32x16(tmem_addr(0u, lq * 32, 208 * wg + 192), o);
+          tmem_wait_ld();
+          tcgen05_fence_before();
+          warp_arrive_a(BAR(A3Bars::OF + wg));
+          const float den = __uint_as_float(o[8]);   // sum of the rounded probabilities; P_ii = 1, so den >= 1
+          overflow |= !(den < 1e30f) || !(den > 0.25f);
+          const float inv = __frcp_rn(den);
+          const int64_t row = (int64_t)chunk * 256 + wg * 128 + r;
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = fmaf(__uint_as_float(o[i]), inv, bv[i]);
+          *reinterpret_cast<uint4*>(o16 + row * 64 + (g * 4 + hh) * 8) =
+              make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+        }
+      }
+      if (__any_sync(0xffffffffu, overflow) && lane == 0) {
+        unit_flags[unit] = 1;
+        atomicAdd(n_flagged, 1);
+      }
+      // every accumulator of the unit has been read: all its MMAs are complete, the operand buffer may be refilled
+      warp_arrive_a(BAR(A3Bars::DONE + (it & 1)));
+    }
+    A3PH(1);
+    if (warp == 20) A3PH_FLUSH(12, 2);
   } else {
-    if (warp == 12 || warp == 13) {
+    if (warp == 24 || warp == 25) {
       // =============================== MMA issue warps ============================================
-      const uint32_t wg = (uint32_t)(warp - 12);
+      const uint32_t wg = (uint32_t)(warp - 24);
       const uint32_t idesc_s = umma_idesc(128, 64, kFmtF16), idesc_o = umma_idesc(128, 16, kFmtF16);
       const uint32_t tS = 208u * wg, tO = 208u * wg + 192u;
       const uint64_t d0 = umma_desc_k_sw128(smem_u32(smem));
@@ -355,9 +343,10 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
           if (elect_one()) {   // O += P_q V_h over the quarter's 64 keys: 4 K-steps, A operand straight from TMEM
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_f16_ts(tO, tS + 64u * slot + 8u * ks, dV + (uint64_t)((q * 8192 + hh * 2048 + ks * 32) >> 4), idesc_o,
+              umma_f16_ts(tO, tS + 64u * slot + 32u * (ks >> 1) + 8u * (ks & 1), dV + (uint64_t)((q * 8192 + hh * 2048 + ks * 32) >> 4), idesc_o,
                           (q > 0 || ks > 0) ? 1u : 0u);
             umma_commit_a(BAR(A3Bars::PV + 3 * wg + slot));
+            if (q == 3) umma_commit_a(BAR(A3Bars::OR + wg));   // the head's O is complete: output warpgroup
           }
           __syncwarp();
           A3PH(1);
@@ -379,8 +368,8 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
           }
         }
       }
-      if (warp == 12) A3PH_FLUSH(6, 6);
-    } else if (warp == 14) {
+      if (warp == 24) A3PH_FLUSH(6, 6);
+    } else if (warp == 26) {
       // =============================== TMA + QKV projection warp ==================================
       const uint32_t idesc_qkv = umma_idesc(128, 96, kFmtF16);
       const uint64_t d0 = umma_desc_k_sw128(smem_u32(smem));

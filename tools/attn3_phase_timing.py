@@ -17,9 +17,9 @@ from seq2squiggle_b200.checkpoint import random_init_checkpoint, set_config  # n
 from seq2squiggle_b200.engine import Engine  # noqa: E402
 
 NAMES = {0: "softmax: wait S (+ld issue)", 1: "softmax: tcgen05.wait::ld", 2: "softmax: exp + st issue",
-         3: "softmax: O read / normalise / store", 4: "softmax: wait::st + arrive P", 5: "softmax: unit boundary",
+         3: "softmax: (unused)", 4: "softmax: wait::st + arrive P", 5: "softmax: unit boundary",
          6: "MMA warp: wait P", 7: "MMA warp: issue P.V", 8: "MMA warp: wait P.V done", 9: "MMA warp: issue S",
-         10: "MMA warp: wait O read", 11: "MMA warp: wait K/V (unit start)", 14: "producer: wait QKV MMA",
+         10: "MMA warp: wait O read", 11: "MMA warp: wait K/V (unit start)", 12: "output warp: wait P.V of the last quarter", 13: "output warp: read / normalise / store", 14: "producer: wait QKV MMA",
          15: "producer: epilogue"}
 
 cfg = set_config(None)
@@ -42,7 +42,7 @@ lib.s2s_debug_counters(out, 16, 1)
 v = np.array(list(out), dtype=np.float64)
 units = 2.0 * nc * 2   # (chunk, head group) x 2 decoder layers
 print(f"chunks {nc}, step {e0.elapsed_time(e1):.2f} ms, units {units:.0f}")
-for lo, hi, who in ((0, 6, "softmax warp 0"), (6, 12, "MMA warp 12"), (14, 16, "producer warp 8")):
+for lo, hi, who in ((0, 6, "softmax warp 0"), (6, 12, "MMA warp (tile 0)"), (12, 14, "output warp"), (14, 16, "producer warp")):
     tot = v[lo:hi].sum()
     print(f"{who}: {tot / units:.0f} clk/unit")
     for i in range(lo, hi):
