@@ -30,7 +30,7 @@
 
 constexpr int kAttn3Threads = 864;   // 27 warps, 72 registers per thread; no setmaxnreg (the pool of a CTA is what it was launched with)
 #ifndef S2S_POLY3_H2
-#define S2S_POLY3_H2 8
+#define S2S_POLY3_H2 6
 #endif
 constexpr int kPoly3H2 = S2S_POLY3_H2;  // pairs of every 16 computed by the packed-fp16 polynomial instead of MUFU.EX2
 constexpr int kA3Unit = 6 * kSlab;      // bytes of one operand buffer: Q (2 tiles) | K (256 keys) | V^T (4 quarters)
