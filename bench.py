@@ -31,10 +31,16 @@ FLOP_PER_CHUNK = 85_083_392
 ATT_FLOP_PER_CHUNK_LAYER = 16_000_000       # QK^T 8.0 M + PV 8.0 M per decoder layer
 ATT_EXP_PER_CHUNK_LAYER = 8 * 250 * 250     # softmax exponentials per decoder layer
 MUFU_PER_CLK_SM = 16                        # ex2 per clock per SM (4 per SM sub-partition)
-# k_tc_attn2, one launch of 32768 chunks, `ncu --set full` (profiles/r01_attn2_ncu.txt): dram__bytes_read.sum 1.090957 GB
-# + dram__bytes_write.sum 1.043353 GB; the algorithmic traffic is 2 x 256 rows x 128 B = 65,536 B per chunk (x16 in, o16 out)
-ATT_DRAM_BYTES_PER_CHUNK_NCU = (1.090957e9 + 1.043353e9) / 32768
+# k_tc_attn3, one launch of 32768 chunks, `ncu --set full` (profiles/r02_attn3_ncu.txt): dram__bytes_read.sum 0.963865 GB
+# + dram__bytes_write.sum 0.917112 GB; the algorithmic traffic is 2 x 256 rows x 128 B = 65,536 B per chunk (x16 in, o16 out)
+# (ncu's figure is below it: part of the o16 stream of one launch is still in the 126 MB L2 when the counters stop)
+ATT_DRAM_BYTES_PER_CHUNK_NCU = (0.963865e9 + 0.917112e9) / 32768
 ATT_ALGO_BYTES_PER_CHUNK = 2 * 256 * 128
+ATT_QKV_FLOP_PER_CHUNK_LAYER = 2 * 256 * 64 * 192          # fused QKV projection inside the attention kernel
+FFN_FLOP_PER_CHUNK_LAYER = 2 * 256 * 64 * (64 + 256 + 256)  # fc + W1 + W2 per decoder layer (256 rows per chunk)
+FFN_BYTES_PER_CHUNK_LAYER = 256 * 384                       # o16 read + x16 read + x16 written, 128 B per row each
+LR_BYTES_PER_CHUNK = 2048 + 64 + 64 + 32000 + 1000 + 4      # enc_out, sigma, dur in; features, sigma_ext, total out
+COMPACT_BYTES_PER_CHUNK_FIXED = 1000 + 4 + 8                # pA read, count read, offset written (+ 2 B per emitted sample)
 
 
 def synth_reads(n_reads: int, seed: int, r: int = 1000):
@@ -111,6 +117,9 @@ def default_opts(precision: str, seed: int = 7):
 # ---------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path on the host cores
 # ---------------------------------------------------------------------------------------------------
+CPU_MATMUL_PRECISION = "medium"   # what the reference sets (model.py:22); "highest" is the golden-vector mode
+
+
 def cpu_reference_step(sd, cfg, reads, batch_chunks=1024):
     """One bounded sample of the reference CPU path: tokenise (utils.py:350-356, the reference's Python loops),
     predict_step per DataLoader batch of 1024 chunks (model.py:195-250), export + digitise.  Returns
@@ -119,6 +128,7 @@ def cpu_reference_step(sd, cfg, reads, batch_chunks=1024):
     from oracle import s2s_oracle as orc
     from oracle.profiles_kat import PROFILES
     prof = PROFILES["dna-r10-prom"]
+    torch.set_float32_matmul_precision(CPU_MATMUL_PRECISION)
     t0 = time.perf_counter()
     ids, chunks = [], []
     for i, r in enumerate(reads):
@@ -165,7 +175,9 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(n_reads, None),
             "reads_per_s": tot_r / tot_t, "chunks_per_s": tot_c / tot_t,
-            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample,
+                             "precision": f"fp32 tensors, torch.set_float32_matmul_precision('{CPU_MATMUL_PRECISION}') "
+                                          "as the reference sets it (model.py:22)"},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit_result(line)
 
@@ -197,6 +209,14 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     cfg = set_config(None)
     sd = random_init_checkpoint(cfg, seed=1)["state_dict"]
+    if args.sharp != 1.0:
+        # trained-like regime: W_q / W_k of the decoder scaled (scores grow with the square), so that the fast attention
+        # kernel's fp16 probabilities overflow and units fall back to the exact kernel
+        for layer in range(cfg["decoder_layers"]):
+            for name in ("w_qs", "w_ks"):
+                for part in ("weight", "bias"):
+                    key = f"decoders.layer_stack_FFT.{layer}.slf_attn.{name}.{part}"
+                    sd[key] = sd[key] * args.sharp
     eng = Engine(sd, cfg, device=local)
     opts = default_opts(args.precision)
     lib = _lib.load()
@@ -310,27 +330,64 @@ def run_ours(args):
             "e2e": {"value": e2e_samples / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d / args.steps / world,
                     "d2h_bytes_per_step": d2h / args.steps / world},
             "gpu_launches": int(launches), "clocks": clk}
+    if args.sharp != 1.0:
+        line["config"]["sharp_scale"] = args.sharp
     if kt:
         tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        ach = ATT_FLOP_PER_CHUNK_LAYER * kt["chunks_per_launch"] / (kt["ms_per_launch"] * 1e-3) / 1e12
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
         sm_mhz = (clk or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
-        exp_rate = ATT_EXP_PER_CHUNK_LAYER * kt["chunks_per_launch"] / (kt["ms_per_launch"] * 1e-3)
+        att = kt["attention"]
+        cpl, sec = att["chunks_per_launch"], att["ms_per_launch"] * 1e-3
+        exp_rate = ATT_EXP_PER_CHUNK_LAYER * cpl / sec
         exp_peak = MUFU_PER_CLK_SM * 148 * sm_mhz * 1e6
-        line["roofline"] = {"kernel": "k_tc_attn2 (fused QKV projection + decoder attention)", "bound": "tensor",
-                            "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                            "traffic": ATT_DRAM_BYTES_PER_CHUNK_NCU * kt["chunks_per_launch"],
+        tens = (ATT_FLOP_PER_CHUNK_LAYER + ATT_QKV_FLOP_PER_CHUNK_LAYER) * cpl / sec / 1e12
+        # The dominant kernel: d_k = 8 gives 32 MMA FLOPs per softmax element, so the kernel is bound by the exponentials
+        # (XU pipe: MUFU.EX2 at 16 / clk / SM, shared with the F2FP packs), not by the tensor pipe.  `achieved` / `peak`
+        # are the exponential rate against the MUFU-only rate (part of the exponentials run as a packed-fp16 polynomial
+        # on the FMA pipe, so the fraction can pass 1); the tensor-pipe fraction of the same launches is alongside.
+        line["roofline"] = {"kernel": "k_tc_attn3 (fused QKV projection + decoder attention, one launch = one decoder layer "
+                                      "of one 32768-chunk sub-batch, incl. k_attn_gate and the exact-kernel fallback pass)",
+                            "bound": "xu", "achieved": exp_rate / 1e9, "peak": exp_peak / 1e9, "unit": "Gexp/s",
+                            "frac": exp_rate / exp_peak,
+                            "peak_source": f"16 MUFU.EX2 / clk / SM x 148 SMs x {sm_mhz:.0f} MHz (SM clock sampled in this run)",
+                            "tensor": {"achieved": tens, "peak": tf_peak, "unit": "TFLOP/s", "frac": tens / tf_peak,
+                                       "peak_source": f"{src} bf16_tflops_sustained",
+                                       "note": "QK^T + PV (16.0 MFLOP) + fused QKV projection (6.29 MFLOP) per chunk per layer"},
+                            "traffic": ATT_DRAM_BYTES_PER_CHUNK_NCU * cpl,
                             "traffic_note": "dram__bytes_read+write per launch from the ncu --set full capture "
-                                            "(profiles/r01_attn2_ncu.txt), scaled to this run's chunks per launch; "
-                                            f"algorithmic HBM bytes per launch {ATT_ALGO_BYTES_PER_CHUNK * kt['chunks_per_launch']:.4g}",
-                            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
-                            "launches_timed": kt["launches"], "ms_per_launch": kt["ms_per_launch"],
-                            "share_of_step": kt["share"],
-                            "note": "d_k=8 attention is bound by the softmax exponentials (XU pipe: MUFU.EX2 + F2FP), not by "
-                                    "the tensor pipe; achieved counts attention MMA FLOPs only (QK^T + PV, 16 MFLOP per "
-                                    "chunk per layer); exp.achieved counts all exponentials although a quarter of "
-                                    "them run on the FMA pipe",
-                            "exp": {"achieved_gexp_s": exp_rate / 1e9, "peak_gexp_s": exp_peak / 1e9,
-                                    "frac": exp_rate / exp_peak, "peak": f"16 ex2/clk/SM x 148 SMs x {sm_mhz:.0f} MHz"}}
+                                            "(profiles/r02_attn3_ncu.txt), scaled to this run's chunks per launch; "
+                                            f"algorithmic HBM bytes per launch {ATT_ALGO_BYTES_PER_CHUNK * cpl:.4g}",
+                            "launches_timed": att["launches"], "ms_per_launch": att["ms_per_launch"],
+                            "share_of_step": att["share"]}
+        kernels = []
+        if "ffn" in kt:
+            f = kt["ffn"]
+            ach = FFN_FLOP_PER_CHUNK_LAYER * f["chunks_per_launch"] / (f["ms_per_launch"] * 1e-3) / 1e12
+            kernels.append({"kernel": "k_tc_fc_ffn (fc + LN + FFN + LN; last layer: + out_linear, x165, noise, clamp, count)",
+                            "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                            "hbm_gbs": FFN_BYTES_PER_CHUNK_LAYER * f["chunks_per_launch"] / (f["ms_per_launch"] * 1e-3) / 1e9,
+                            "ms_per_launch": f["ms_per_launch"], "launches_timed": f["launches"], "share_of_step": f["share"]})
+        if "length_regulate" in kt:
+            f = kt["length_regulate"]
+            ach = LR_BYTES_PER_CHUNK * f["chunks_per_launch"] / (f["ms_per_launch"] * 1e-3) / 1e9
+            kernels.append({"kernel": "k_length_regulate16", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": ach / hbm_peak, "ms_per_launch": f["ms_per_launch"], "launches_timed": f["launches"],
+                            "share_of_step": f["share"]})
+        if "compact" in kt:
+            f = kt["compact"]
+            byt = (COMPACT_BYTES_PER_CHUNK_FIXED + 2.0 * samples / max(chunks, 1)) * f["chunks_per_launch"]
+            ach = byt / (f["ms_per_launch"] * 1e-3) / 1e9
+            kernels.append({"kernel": "zero-strip compaction + digitisation (scan x3, k_read_offsets, k_compact)",
+                            "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                            "ms_per_launch": f["ms_per_launch"], "launches_timed": f["launches"], "share_of_step": f["share"]})
+        for name in ("encoder", "front_end"):
+            if name in kt:
+                f = kt[name]
+                kernels.append({"kernel": name, "ms_per_launch": f["ms_per_launch"], "launches_timed": f["launches"],
+                                "share_of_step": f["share"]})
+        line["kernels"] = kernels
+        line["peaks"] = {"hbm_gbs": hbm_peak, "bf16_tflops_sustained": tf_peak, "source": src}
     if args.cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
@@ -339,32 +396,81 @@ def run_ours(args):
         n, c, t = cpu_reference_step(sd, cfg, rd)
         line["cpu_baseline"] = {"value": n / t, "unit": "samples/s", "cores": cores, "kind": "port",
                                 "sample": f"{args.ref_reads} reads ({c} chunks) of the same distribution, oracle port "
-                                          f"of the reference CPU path incl. its Python tokeniser, {t:.1f} s"}
+                                          f"of the reference CPU path incl. its Python tokeniser, {t:.1f} s",
+                                "precision": f"fp32 tensors, torch.set_float32_matmul_precision('{CPU_MATMUL_PRECISION}') "
+                                             "as the reference sets it (model.py:22)"}
+    if args.gpu_eager_baseline and world == 1:
+        line["gpu_eager_baseline"] = gpu_eager_baseline(sd, cfg, dev, samples / max(chunks, 1))
     emit_result(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def kernel_timing(eng, lib, step, i):
-    """CUDA-event time of every k_tc_attention launch of one step (the library brackets the launches itself)."""
+    """CUDA-event time of the kernel groups of one step (the library brackets its own launches on the launching
+    stream, s2s_profile_kernel / s2s_profile_kernel_group)."""
     import ctypes as C
     import torch
-    if not hasattr(lib, "s2s_profile_kernel"):
+    if not hasattr(lib, "s2s_profile_kernel_group"):
         return None
+    sig = [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.s2s_profile_kernel.restype = C.c_int
-    lib.s2s_profile_kernel.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
-    ms, n, ch = C.c_double(), C.c_int64(), C.c_int64()
+    lib.s2s_profile_kernel.argtypes = [C.c_void_p, C.c_int] + sig
+    lib.s2s_profile_kernel_group.restype = C.c_int
+    lib.s2s_profile_kernel_group.argtypes = [C.c_void_p, C.c_char_p] + sig
     lib.s2s_profile_kernel(eng.handle, 1, None, None, None)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     step(i)
     e1.record()
     torch.cuda.synchronize()
-    lib.s2s_profile_kernel(eng.handle, 0, C.byref(ms), C.byref(n), C.byref(ch))
-    if n.value == 0:
-        return None
-    return {"ms_per_launch": ms.value / n.value, "launches": int(n.value), "chunks_per_launch": ch.value / n.value,
-            "share": ms.value / e0.elapsed_time(e1)}
+    step_ms = e0.elapsed_time(e1)
+    out = {}
+    for name in ("attention", "ffn", "length_regulate", "compact", "encoder", "front_end"):
+        ms, n, ch = C.c_double(), C.c_int64(), C.c_int64()
+        if lib.s2s_profile_kernel_group(eng.handle, name.encode(), C.byref(ms), C.byref(n), C.byref(ch)) != 0 or n.value == 0:
+            continue
+        out[name] = {"ms_per_launch": ms.value / n.value, "launches": int(n.value), "chunks_per_launch": ch.value / n.value,
+                     "share": ms.value / step_ms}
+    lib.s2s_profile_kernel(eng.handle, 0, None, None, None)
+    return out if "attention" in out else None
+
+
+def gpu_eager_baseline(sd, cfg, dev, samples_per_chunk):
+    """The reference's own GPU mode (inference.py:404: Lightning precision "16-mixed"): the oracle's encoder + length
+    regulator + decoder in eager PyTorch under fp16 autocast on this GPU, DataLoader batches of 1024 chunks
+    (--predict-batch-size default), model only (no tokeniser, no samplers, no writer): the number the kernels must beat."""
+    import torch
+    from oracle import s2s_oracle as orc
+    k = cfg["seq_kmer"]
+    g = torch.Generator().manual_seed(3)
+    codes = torch.randint(1, 5, (1024, 16, k), generator=g)
+    data = torch.nn.functional.one_hot(codes, 5).to(torch.float16).reshape(1024, 16, 5 * k).to(dev)
+    dur = np.full((1024, 16), 12, dtype=np.int32)
+    j = torch.from_numpy(orc.lr_expand_indices(dur, 250)).to(dev).long()
+    sd_dev = {key: v.to(dev) for key, v in sd.items() if torch.is_tensor(v)}
+
+    def eager(x):
+        with torch.inference_mode(), torch.autocast("cuda", dtype=torch.float16):
+            enc, _ = orc.encoder_forward(sd_dev, cfg, x)
+            lr = torch.where(j[..., None] >= 0, torch.gather(enc.float(), 1, j.clamp(min=0)[..., None].expand(-1, -1, 64)), 0.0)
+            return orc.decoder_forward(sd_dev, cfg, lr).squeeze(-1).float() * 165.0
+
+    for _ in range(3):
+        eager(data)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_it = 20
+    e0.record()
+    for _ in range(n_it):
+        eager(data)
+    e1.record()
+    torch.cuda.synchronize()
+    dt = e0.elapsed_time(e1) * 1e-3 / n_it
+    return {"what": "oracle encoder + length regulator + decoder, eager PyTorch under torch.autocast(float16) on this GPU "
+                    "(the reference's GPU mode, inference.py:404), 1024-chunk batches, model only",
+            "ms_per_batch": dt * 1e3, "chunks_per_s": 1024 / dt, "value": 1024 / dt * samples_per_chunk, "unit": "samples/s",
+            "note": "samples/s = chunks/s x this run's emitted samples per chunk"}
 
 
 _RESULT_FD = None
@@ -389,6 +495,10 @@ def main():
     ap.add_argument("--reads-per-step", type=int, default=4000)
     ap.add_argument("--ref-reads", type=int, default=200, help="reads per CPU-arm step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-gpu-eager-baseline", dest="gpu_eager_baseline", action="store_false",
+                    help="skip timing the reference's own GPU mode (oracle modules, eager PyTorch, fp16 autocast)")
+    ap.add_argument("--sharp", type=float, default=1.0,
+                    help="scale W_q / W_k of the decoder (trained-like sharp attention: exercises the exact-kernel fallback)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

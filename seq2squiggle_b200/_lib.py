@@ -17,7 +17,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 EXPORTS = ["s2s_last_error", "s2s_abi_version", "s2s_weights_count", "s2s_create", "s2s_destroy",
            "s2s_workspace_bytes", "s2s_chunks_of_read", "s2s_forward_reads", "s2s_forward_chunks",
-           "s2s_check", "s2s_length_regulate", "s2s_digitise", "s2s_compact_reads", "s2s_profile_kernel", "s2s_launch_count", "s2s_debug_counters"]
+           "s2s_check", "s2s_length_regulate", "s2s_digitise", "s2s_compact_reads", "s2s_profile_kernel", "s2s_profile_kernel_group", "s2s_launch_count", "s2s_debug_counters"]
 
 
 class S2SConfig(C.Structure):

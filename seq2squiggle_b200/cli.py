@@ -45,13 +45,29 @@ def set_seeds(seed: int) -> int:
     streams are keyed by ``torch.initial_seed()``)."""
     import torch
     if not seed:
-        seed = int.from_bytes(os.urandom(4), byteorder="big", signed=False)
+        seed = resolve_random_seed()
         logger.info(f"No seed provided. Generated random seed: {seed}")
     logger.info(f"Setting all random seeds to {seed}")
     os.environ["PYTHONHASHSEED"] = str(seed)
     random.seed(seed)
     torch.manual_seed(seed)
     np.random.seed(seed)
+    return seed
+
+
+def resolve_random_seed() -> int:
+    """``-s 0``: one random seed for the whole run.  Under ``torchrun`` every rank derives the read list, the shard
+    bounds, the read numbers and the device Philox key from the seed, so rank 0 draws it and broadcasts it over the
+    gloo control plane; ranks drawing their own would simulate different (overlapping / missing) reads."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    seed = int.from_bytes(os.urandom(4), byteorder="big", signed=False) or 1
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("gloo")
+        box = [seed]
+        dist.broadcast_object_list(box, src=0)
+        seed = int(box[0])
     return seed
 
 

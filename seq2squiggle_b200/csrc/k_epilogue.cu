@@ -1,5 +1,7 @@
 // K-F / K-G: decoder output head, noise, clamp, zero-strip, digitisation and per-read compaction.
 //
+// (fp32 parity path and the stand-alone stage entry points; on the tensor-core path p, x165, noise, clamp and the per-chunk
+//  non-zero count are fused into the last FFN kernel's epilogue, k_tc.cu, and only the compaction below remains)
 //   modules.py:140-141   p = ReLU(out_linear(y))
 //   model.py:221-240     pA = 165 p; where pA != 0: += N(0, clamp(sigma_ext,min_noise)*noise_std*165)  (sampler)
 //                                                     or N(0, noise_std)                                  (static)
@@ -52,29 +54,6 @@ __global__ void __launch_bounds__(256) k_out_epilogue(const float* __restrict__ 
       }
       pa[idx] = fmaxf(v_pa, 0.f);
     }
-  }
-}
-
-// Tensor-core path: p = ReLU(out_linear(.)) was already produced by the last FFN kernel (one float per row, 256 rows per
-// chunk); this is the x165 / noise / clamp of model.py:221-240 on 250 positions per chunk.
-__global__ void __launch_bounds__(256) k_noise_epilogue(const float* __restrict__ p_rows, const float* __restrict__ sigma_ext,
-                                                        int64_t n_pos, float scaling, s2s_run_opts o,
-                                                        float* __restrict__ p_tap, float* __restrict__ pa) {
-  const Philox ph(o.seed);
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_pos; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = idx / S2S_L_DEC;
-    const int t = (int)(idx - c * S2S_L_DEC);
-    const float p = p_rows[c * S2S_L_DEC_PAD + t];
-    if (p_tap) p_tap[idx] = p;
-    float v_pa = p * scaling;
-    if (o.noise_mode != S2S_NOISE_OFF && v_pa != 0.f) {
-      const uint64_t gc = o.chunk_id_base + (uint64_t)c;
-      uint4 r = ph((uint32_t)gc, (uint32_t)(gc >> 32), (uint32_t)t, kStreamNoise);
-      float z = box_muller(r.x, r.y).x;
-      float sd = o.noise_mode == S2S_NOISE_SAMPLER ? fmaxf(sigma_ext[idx], o.min_noise) * o.noise_std * scaling : o.noise_std;
-      v_pa += z * sd;
-    }
-    pa[idx] = fmaxf(v_pa, 0.f);
   }
 }
 
@@ -212,17 +191,6 @@ int launch_out_epilogue(const DevWeights& w, const float* y, const float* sigma_
   return 0;
 }
 
-int launch_noise_epilogue(const DevWeights& w, const float* p_rows, const float* sigma_ext, int64_t n_chunks,
-                          const s2s_run_opts& o, float* p_tap, float* pa, cudaStream_t st) {
-  if (n_chunks == 0) return 0;
-  const int64_t n_pos = n_chunks * S2S_L_DEC;
-  int64_t blocks = ceil_div(n_pos, 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  k_noise_epilogue<<<(unsigned)blocks, 256, 0, st>>>(p_rows, sigma_ext, n_pos, w.cfg.scaling_max_value, o, p_tap, pa);
-  S2S_LAUNCH_CHECK();
-  return 0;
-}
-
 int launch_digitise(const float* pa, int64_t n, float dig, float range, float offset, int16_t* raw, cudaStream_t st) {
   if (n == 0) return 0;
   int64_t blocks = ceil_div(n, 256);
@@ -239,7 +207,7 @@ int64_t compact_workspace_bytes(int64_t n_chunks) {
 
 int launch_compact(const float* pa, const int64_t* chunk_offsets, int64_t n_reads, int64_t n_chunks, float dig,
                    float range, float offset, int rna_reverse, void* ws, int64_t ws_bytes, int16_t* raw,
-                   int64_t* raw_offsets, cudaStream_t st) {
+                   int64_t* raw_offsets, cudaStream_t st, bool counts_ready) {
   if (ws_bytes < compact_workspace_bytes(n_chunks)) {
     set_error("launch_compact: workspace too small (%lld < %lld)", (long long)ws_bytes,
               (long long)compact_workspace_bytes(n_chunks));
@@ -255,8 +223,10 @@ int launch_compact(const float* pa, const int64_t* chunk_offsets, int64_t n_read
   int64_t* chunk_out = reinterpret_cast<int64_t*>(p); p += align_up((n_chunks + 1) * 8, 256);
   int64_t* tile_sums = reinterpret_cast<int64_t*>(p);
   const unsigned warp_blocks = (unsigned)ceil_div(n_chunks, 8);
-  k_count_nonzero<<<warp_blocks, 256, 0, st>>>(pa, n_chunks, counts);
-  S2S_LAUNCH_CHECK();
+  if (!counts_ready) {   // fp32 path / stand-alone compaction: count here; the tensor-core decoder counts in its epilogue
+    k_count_nonzero<<<warp_blocks, 256, 0, st>>>(pa, n_chunks, counts);
+    S2S_LAUNCH_CHECK();
+  }
   k_scan_tile_sums<<<(unsigned)n_tiles, 256, 0, st>>>(counts, n_chunks, tile_sums);
   S2S_LAUNCH_CHECK();
   k_scan_tiles_serial<<<1, 32, 0, st>>>(tile_sums, n_tiles);

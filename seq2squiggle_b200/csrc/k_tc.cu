@@ -27,6 +27,7 @@ using namespace tc;
 namespace {
 
 constexpr uint32_t kWaitLimit = 1u << 22;
+constexpr uint32_t kStreamNoiseTc = 0x5D0003u;   // the Philox stream of the noise draw (k_epilogue.cu: kStreamNoise)
 constexpr int kSlab = 128 * 128;  // bytes of one [128 rows x 128 B] tile
 
 // status codes written on a barrier timeout
@@ -135,26 +136,11 @@ __device__ __forceinline__ void chunk_exp_store(const uint32_t (&r)[32], float s
   tmem_st_32x16(taddr, pk);
 }
 
-// 2^x on the FMA/ALU pipes instead of MUFU (the attention kernel is bound by the 16 ex2/clk/SM of the XU pipe):
-// round-to-nearest split x = n + f with the 1.5*2^23 magic constant, degree-3 minimax polynomial for 2^f on
-// [-0.5, 0.5] (max relative error 7.5e-5, well under the 4.9e-4 half-ulp of the fp16 P it is rounded to), exponent
-// add by one integer LEA.  Clamped to [-30, 64]: below is 0 in fp16 anyway, above still overflows fp16 to inf, which is
-// what flags the unit for the exact kernel.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fminf(fmaxf(x, -30.0f), 64.0f);
-  const float t = x + 12582912.0f;
-  const float f = x - (t - 12582912.0f);
-  float p = fmaf(0.05517167f, f, 0.24261113f);
-  p = fmaf(p, f, 0.69326097f);
-  p = fmaf(p, f, 0.99992806f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
 // 2^x for a PAIR of scores in packed fp16 arithmetic (HFMA2 / HADD2 on the FMA pipe, no MUFU).  P is rounded to fp16
 // for the P.V MMA anyway; here the argument is rounded to fp16 first (|x| < 16: absolute error <= 2^-8, i.e. a relative
 // error of P of at most 0.27 %, 0.07 % for |x| < 4).  n = rint(x) comes from the magic constant 1536 + 15: the low five
 // mantissa bits of t = x + 1551 are n + 15, which is the fp16 exponent field of 2^n, so 2^n is one shift + mask and the
-// result is p(f) * 2^n by one HMUL2.  Degree-3 polynomial for 2^f on [-0.5, 0.5].  x is clamped to [-15, 16]:
+// result is p(f) * 2^n by one HMUL2.  Degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5).  x is clamped to [-15, 16]:
 // 2^-15 * p rounds to <= 3.1e-5 (the row's largest P is >= 1), and n = 16 gives the exponent field 31 = inf, which the
 // denominator check turns into the exact-kernel fallback exactly like an overflowing MUFU result.
 __device__ __forceinline__ uint32_t ex2_poly_h2(float x0, float x1) {
@@ -170,41 +156,17 @@ __device__ __forceinline__ uint32_t ex2_poly_h2(float x0, float x1) {
   return *reinterpret_cast<const uint32_t*>(&r);
 }
 
-// chunk_exp_store with part of the exponentials taken off the MUFU pipe (evenly interleaved):
-//   kPoly  > 0: kPoly of every 32 single exponentials by the fp32 polynomial ex2_poly;
-//   kPolyH > 0: kPolyH of every 16 PAIRS by the packed-fp16 polynomial ex2_poly_h2.
-template <int kValid, int kPoly, int kPolyH = 0>
-__device__ __forceinline__ void chunk_exp_store_mixed(const uint32_t (&r)[32], float scale, float mneg, uint32_t taddr) {
-  uint32_t pk[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    if (kPolyH > 0 && 2 * i + 1 < kValid && (i * kPolyH) % 16 < kPolyH) {
-      pk[i] = ex2_poly_h2(fmaf(__uint_as_float(r[2 * i]), scale, mneg), fmaf(__uint_as_float(r[2 * i + 1]), scale, mneg));
-      continue;
-    }
-    float p[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int e = 2 * i + h;
-      const float x = fmaf(__uint_as_float(r[e]), scale, mneg);
-      p[h] = e < kValid ? (((e * kPoly) % 32 < kPoly) ? ex2_poly(x) : ex2_approx(x)) : 0.f;
-    }
-    pk[i] = pack_half2(p[0], p[1]);
-  }
-  tmem_st_32x16(taddr, pk);
-}
-
 __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUtensorMap tmX,
                                                     const __grid_constant__ CUtensorMap tmWg,
                                                     const float* __restrict__ bias_g, __half* __restrict__ o16,
                                                     int n_units, const int* __restrict__ unit_flags,
                                                     const int* __restrict__ n_flagged, int* status,
                                                     int* __restrict__ hint_out = nullptr) {
-  // As the exact fallback of k_tc_attn2 (unit_flags != nullptr) only the flagged units are recomputed.
+  // As the exact fallback of k_tc_attn3 (unit_flags != nullptr) only the flagged units are recomputed.
   if (unit_flags) {
     const int nf = *n_flagged;
     // n_flagged counts flagging WARPS (up to 4 per unit).  More than half of them: this layer's attention is too sharp
-    // for the single-reference kernel; the hint makes the next sub-batches skip it (see k_tc_attn2).
+    // for the single-reference kernel; the hint makes the next sub-batches skip it (see k_tc_attn3).
     if (hint_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *hint_out = nf > 2 * n_units ? 1 : 0;
     if (nf == 0) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_phase[12], (unsigned long long)nf);
@@ -427,12 +389,11 @@ __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUte
 #define PHF_FLUSH do {} while (0)
 #endif
 
-#include "k_tc_attn2.cuh"
 
-// Adaptive fallback gate, launched in front of k_tc_attn2.  When the previous sub-batch of this layer sent most of its
+// Adaptive fallback gate, launched in front of k_tc_attn3.  When the previous sub-batch of this layer sent most of its
 // units to the exact kernel (hint set by k_tc_attn), running the single-reference kernel first only wastes its time
 // (measured with W_q, W_k scaled x4: 1.21 M chunks/s with both kernels, 1.95 M with the exact kernel alone): every
-// unit is flagged here and status[1] tells k_tc_attn2 to return at once.  The host re-probes every 16th call.
+// unit is flagged here and status[1] tells k_tc_attn3 to return at once.  The host re-probes every 16th call.
 __global__ void k_attn_gate(const int* __restrict__ hint, int probe, int n_units, int* __restrict__ unit_flags,
                             int* __restrict__ n_flagged, int* __restrict__ status) {
   const bool skip = !probe && *hint != 0;
@@ -443,7 +404,6 @@ __global__ void k_attn_gate(const int* __restrict__ hint, int probe, int n_units
     if (skip) *n_flagged = 4 * n_units;
   }
 }
-#include "k_tc_attn4.cuh"
 #include "k_tc_attn3.cuh"
 
 // =================================================================================================
@@ -464,7 +424,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
                                                       const __grid_constant__ CUtensorMap tmW2,
                                                       const __grid_constant__ CUtensorMap tmXout,
                                                       const __grid_constant__ FfnParams P, float* __restrict__ x32,
-                                                      __half* __restrict__ x16, float* __restrict__ p_out,
+                                                      __half* __restrict__ x16, const __grid_constant__ OutEpi E,
                                                       int n_tiles, int* status) {
   // The per-column vectors (three biases, two LayerNorm affine pairs, out_linear) arrive as a __grid_constant__ kernel
   // parameter: every use below has a compile-time index, so they are constant-bank operands of the FADD / FFMA itself
@@ -676,10 +636,38 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
       layernorm_store<kRes32, !kOutHead>(y, P.g2, P.be2, x32 + row * 64, x16 + row * 64);
     }
     if (kOutHead) {
+      // Fused output epilogue (modules.py:140-141, model.py:221-240): p = ReLU(out_linear), pA = 165 p, Philox noise
+      // where pA != 0, clamp at 0 — written ONCE as fp32 pA, 250 positions per chunk, plus the chunk's count of non-zero
+      // samples (what the zero-strip compaction scans); pad rows 250..255 emit nothing.
       float acc = P.bout;
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc = fmaf(y[i], P.wout[i], acc);
-      p_out[row] = fmaxf(acc, 0.f);
+      const int64_t c = row >> 8;
+      const int t = (int)(row & 255);
+      bool nz = false;
+      if (t < S2S_L_DEC) {
+        const int64_t idx = c * S2S_L_DEC + t;
+        const float p = fmaxf(acc, 0.f);
+        if (E.p_tap) E.p_tap[idx] = p;
+        float v_pa = p * E.scaling;
+        if (E.o.noise_mode != S2S_NOISE_OFF && v_pa != 0.f) {
+          const Philox ph(E.o.seed);
+          const uint64_t gc = E.o.chunk_id_base + (uint64_t)c;
+          const uint4 rr = ph((uint32_t)gc, (uint32_t)(gc >> 32), (uint32_t)t, kStreamNoiseTc);
+          const float z = box_muller(rr.x, rr.y).x;
+          const float sd = E.o.noise_mode == S2S_NOISE_SAMPLER
+                               ? fmaxf(E.sigma_ext[idx], E.o.min_noise) * E.o.noise_std * E.scaling   // model.py:228-230
+                               : E.o.noise_std;                                                        // model.py:236
+          v_pa += z * sd;
+        }
+        v_pa = fmaxf(v_pa, 0.f);
+        E.pa[idx] = v_pa;
+        nz = v_pa != 0.f;
+      }
+      if (E.counts) {   // a warp's 32 rows belong to one chunk (256 rows per chunk)
+        const unsigned m = __ballot_sync(0xffffffffu, nz);
+        if ((tid & 31) == 0 && m) atomicAdd(E.counts + c, __popc(m));
+      }
     }
     __syncthreads();  // all TMEM reads are done before the next tile's MMA overwrites the accumulators
     tcgen05_fence_after();
@@ -823,12 +811,9 @@ int tc_init(TcState& s, const DevWeights& w, int device) {
   }
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_qkv_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemQkv));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt));
-  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
-  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
-  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn4, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn3, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt3));
-  if (const char* env = getenv("S2S_ATTN_V1")) s.attn_v1 = atoi(env) != 0;
-  if (const char* env = getenv("S2S_ATTN_V2")) s.attn_v1 = atoi(env) == 0;
+  if (const char* env = getenv("S2S_ATTN_EXACT")) s.attn_exact = atoi(env) != 0;   // tests: the exact kernel on its own
+  if (const char* env = getenv("S2S_ATTN_V1")) s.attn_exact = atoi(env) != 0;      // (older spelling)
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
@@ -843,7 +828,7 @@ void tc_destroy(TcState& s) {
   s.d_status = nullptr;
 }
 
-int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* p_out, int64_t n_chunks, cudaStream_t st) {
+int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, const OutEpi& epi, int64_t n_chunks, cudaStream_t st) {
   if (n_chunks == 0) return 0;
   EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(s.encode_tiled);
   const uint64_t rows = (uint64_t)n_chunks * S2S_L_DEC_PAD;
@@ -873,63 +858,35 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* p_out
       set_error("cuTensorMapEncodeTiled failed for a weight tensor");
       return -1;
     }
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (s.prof_on) {
-      cudaEventCreate(&e0); cudaEventCreate(&e1);
-      cudaEventRecord(e0, st);
-    }
-    if (s.attn_v1) {
+    cudaEvent_t e0 = prof_begin(s, st);
+    if (s.attn_exact) {
       k_tc_attn<<<grid_att, 128, kSmemAtt, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, nullptr, nullptr, s.d_status);
     } else {
-      // fast kernel (one reference max per row) + exact recomputation of the units whose fp16 P overflowed
+      // fast kernel (reference = the row's own score, folded into the S MMA) + exact recomputation of the units whose
+      // fp16 P overflowed.  Per-layer hint words live behind the status word: when most units of the previous
+      // sub-batch overflowed, k_attn_gate sends everything straight to the exact kernel; every 16th call probes again.
       S2S_CUDA_OK(cudaMemsetAsync(d_flags, 0, (size_t)(n_units + 1) * sizeof(int), st));
-      static const bool one_cta = getenv("S2S_ATTN_1CTA") && atoi(getenv("S2S_ATTN_1CTA"));
-      const int grid2a = one_cta ? (n_units < s.sm_count ? n_units : s.sm_count) : grid_att;
-      const int smem2a = one_cta ? 150 * 1024 : kSmemAtt;
-      // S2S_ATTN_VER=4 selects k_tc_attn4 (16 softmax warps per SM): parity-green but measured SLOWER than k_tc_attn2
-      // (2.96 vs 2.40 ms per 16384 chunks): with 4-5 busy warps per scheduler the MMA issue warps get too few issue slots
-      // and the softmax warps wait for S (profiles/r01_attn4_experiment.txt).
-      static const int attn_ver = getenv("S2S_ATTN_VER") ? atoi(getenv("S2S_ATTN_VER")) : 3;
-      // S2S_ATTN_BOUND=1: Cauchy-Schwarz reference folded into the S MMA (k_tc_attn2<true>): parity-green, no scaling FFMA
-      // and no row-max pass, but measured no faster (4.76 vs 4.76-4.92 ms per 32768 chunks): the exp pass is bound by the
-      // XU pipe, which also executes the F2FP packs (8 (1 - f) + 1 clk per exponential per scheduler).
-      static const int attn_bound = getenv("S2S_ATTN_BOUND") ? atoi(getenv("S2S_ATTN_BOUND")) : 0;
-      // per-layer hint words live behind the status word; every 16th call probes the fast kernel again
       int* hint = s.d_status + 8 + l;
-      if (attn_ver != 4)
-        k_attn_gate<<<64, 256, 0, st>>>(hint, s.attn_calls % 16 == 15, n_units, d_flags + 1, d_flags, s.d_status);
-      if (attn_ver == 3) {
-        // one 512-thread CTA per SM; an even grid keeps every CTA on one head group
-        int grid3 = s.sm_count & ~1;
-        if (grid3 > n_units) grid3 = n_units;
-        k_tc_attn3<<<grid3, kAttn3Threads, kSmemAtt3, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags,
-                                                             s.d_status);
-      } else if (attn_ver != 4 && attn_bound)
-        k_tc_attn2<true><<<grid2a, kAttn2Threads, smem2a, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags,
-                                                                   s.d_status);
-      else if (attn_ver != 4)
-        k_tc_attn2<false><<<grid2a, kAttn2Threads, smem2a, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags,
-                                                                    s.d_status);
-      else
-        k_tc_attn4<<<grid_att, kAttn4Threads, kSmemAtt, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags,
-                                                              s.d_status);
+      k_attn_gate<<<64, 256, 0, st>>>(hint, s.attn_calls % 16 == 15, n_units, d_flags + 1, d_flags, s.d_status);
       S2S_LAUNCH_CHECK();
-      k_tc_attn<<<grid_att, 128, kSmemAtt, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags, s.d_status,
-                                                 attn_ver != 4 ? hint : nullptr);
+      // one 864-thread CTA per SM; an even grid keeps every CTA on one head group
+      int grid3 = s.sm_count & ~1;
+      if (grid3 > n_units) grid3 = n_units;
+      k_tc_attn3<<<grid3, kAttn3Threads, kSmemAtt3, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags, s.d_status);
+      S2S_LAUNCH_CHECK();
+      k_tc_attn<<<grid_att, 128, kSmemAtt, st>>>(tmX, tmWg, bl.bg, b.o16, n_units, d_flags + 1, d_flags, s.d_status, hint);
     }
     S2S_LAUNCH_CHECK();
-    if (s.prof_on) {
-      cudaEventRecord(e1, st);
-      s.prof_events.push_back(e0); s.prof_events.push_back(e1);
-      s.prof_chunks += n_chunks;
-    }
+    prof_end(s, PROF_ATTN, e0, n_chunks, st);
+    e0 = prof_begin(s, st);
     if (l + 1 < w.cfg.decoder_layers)
-      k_tc_fc_ffn<false, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, nullptr, b.x16, nullptr,
+      k_tc_fc_ffn<false, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, nullptr, b.x16, epi,
                                                              n_tiles, s.d_status);
     else
-      k_tc_fc_ffn<false, true><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, nullptr, b.x16, p_out,
+      k_tc_fc_ffn<false, true><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, nullptr, b.x16, epi,
                                                             n_tiles, s.d_status);
     S2S_LAUNCH_CHECK();
+    prof_end(s, PROF_FFN, e0, n_chunks, st);
   }
   return 0;
 }
@@ -968,7 +925,7 @@ int tc_encoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, 
     k_tc_qkv_plain<<<grid2, 128, kSmemQkv, st>>>(tmX, tmWqkv, bl.bqkv, qkv16, (int64_t)rows, s.d_status);
     S2S_LAUNCH_CHECK();
     if (launch_attention_enc_f16(qkv16, o16, n_chunks, st)) return -1;
-    k_tc_fc_ffn<true, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, x32, x16, nullptr, n_tiles,
+    k_tc_fc_ffn<true, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, x32, x16, OutEpi{}, n_tiles,
                                                            s.d_status);
     S2S_LAUNCH_CHECK();
   }
@@ -976,26 +933,47 @@ int tc_encoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, 
   return 0;
 }
 
+cudaEvent_t prof_begin(TcState& s, cudaStream_t st) {
+  if (!s.prof_on) return nullptr;
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, st);
+  return e;
+}
+
+void prof_end(TcState& s, int kind, cudaEvent_t e0, int64_t chunks, cudaStream_t st) {
+  if (!s.prof_on || !e0) return;
+  cudaEvent_t e1 = nullptr;
+  cudaEventCreate(&e1);
+  cudaEventRecord(e1, st);
+  s.prof_recs.push_back({kind, e0, e1, chunks});
+}
+
+int tc_profile_kind(TcState& s, int kind, double* ms_total, int64_t* launches, int64_t* chunks) {
+  S2S_CUDA_OK(cudaDeviceSynchronize());
+  double tot = 0;
+  int64_t n = 0, ch = 0;
+  for (const auto& r : s.prof_recs) {
+    if (r.kind != kind) continue;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    tot += ms; ++n; ch += r.chunks;
+  }
+  if (ms_total) *ms_total = tot;
+  if (launches) *launches = n;
+  if (chunks) *chunks = ch;
+  return 0;
+}
+
 int tc_profile(TcState& s, int enable, double* ms_total, int64_t* launches, int64_t* chunks) {
   if (enable) {
     s.prof_on = true;
-    s.prof_chunks = 0;
     return 0;
   }
   s.prof_on = false;
-  S2S_CUDA_OK(cudaDeviceSynchronize());
-  double tot = 0;
-  for (size_t i = 0; i + 1 < s.prof_events.size(); i += 2) {
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, s.prof_events[i], s.prof_events[i + 1]);
-    tot += ms;
-    cudaEventDestroy(s.prof_events[i]);
-    cudaEventDestroy(s.prof_events[i + 1]);
-  }
-  if (ms_total) *ms_total = tot;
-  if (launches) *launches = (int64_t)(s.prof_events.size() / 2);
-  if (chunks) *chunks = s.prof_chunks;
-  s.prof_events.clear();
+  if (tc_profile_kind(s, PROF_ATTN, ms_total, launches, chunks)) return -1;
+  for (auto& r : s.prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  s.prof_recs.clear();
   return 0;
 }
 

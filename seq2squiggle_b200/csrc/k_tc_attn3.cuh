@@ -16,10 +16,10 @@
 // The softmax reference is folded into the S MMA: every head owns a K=16 operand slice,
 //   A_i = [ c q_i (8) | -m_i, -30000, 0 x 6 ],  B_j = [ k_j (8) | 1, pad_j, 0 x 6 ],   c = log2(e)/sqrt(d_k),
 // so the accumulator holds x_ij = c q_i.k_j - m_i (and about -30000 for the six pad keys 250..255, whose P is exactly 0)
-// and P_ij = 2^x_ij with no scaling FFMA, no row-max pass and no tail special case.  m_i = c q_i.k_i, the row's own
-// (diagonal) score, known in the producer thread that holds both q_i and k_i: softmax is invariant to the reference,
-// P_ii = 1 so the denominator is >= 1, and P only misbehaves when some score exceeds the diagonal one by more than 16
-// (11 nats): then the fp16 P overflows, the row's denominator (accumulated by the tensor core from the same rounded P
+// and P_ij = 2^x_ij with no scaling FFMA, no row-max pass and no tail special case.  m_i = max of the row's own
+// (diagonal) score c q_i.k_i and of its scores against 16 keys spread over the chunk (a [128 x 16] MMA per head and tile
+// against a compact copy of those keys): softmax is invariant to the reference, P_ii <= 1 <= max P so the denominator is >= 1, and P only misbehaves
+// when some score exceeds the reference by more than 16 (11 nats): then the fp16 P overflows, the row's denominator (accumulated by the tensor core from the same rounded P
 // through a ones row of V^T) is inf/NaN, and the unit is flagged and recomputed by the exact two-pass kernel k_tc_attn.
 // K bias is dropped (adds a per-row constant to the scores) and the V bias is added to the normalised output.
 // TMEM columns: query tile g: ring of three 64-column S/P buffers at 208 g + {0, 64, 128}, O accumulator at 208 g + 192
@@ -34,7 +34,8 @@ constexpr int kAttn3Threads = 864;   // 27 warps, 72 registers per thread; no se
 #endif
 constexpr int kPoly3H2 = S2S_POLY3_H2;  // pairs of every 16 computed by the packed-fp16 polynomial instead of MUFU.EX2
 constexpr int kA3Unit = 6 * kSlab;      // bytes of one operand buffer: Q (2 tiles) | K (256 keys) | V^T (4 quarters)
-constexpr int kSmemAtt3 = 2 * kA3Unit + 96 * 128 + 1024;
+constexpr int kA3RefBytes = 16 * 128;   // compact K tile of the 16 reference keys (one per buffer)
+constexpr int kSmemAtt3 = 2 * kA3Unit + 96 * 128 + 2 * kA3RefBytes + 1024;
 constexpr uint32_t kA3QkvCol = 416;
 
 
@@ -64,7 +65,7 @@ __device__ __forceinline__ void exp32_store(const uint32_t (&r)[32], uint32_t ta
 #endif
 
 struct A3Bars {  // indices into the barrier array
-  enum { W = 0, X = 1, QKV = 3, ACC = 4, KV = 5, DONE = 7, S = 9, P = 15, PV = 21, OF = 27, OR = 29, COUNT = 31 };
+  enum { W = 0, X = 1, QKV = 3, ACC = 4, KV = 5, DONE = 7, S = 9, P = 15, PV = 21, OF = 27, OR = 29, KQ = 31, COUNT = 32 };
 };
 
 __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_constant__ CUtensorMap tmX,
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
   __shared__ float s_bias[2][96];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* sW = smem + 2 * kA3Unit;   // [96 x 128 B] weight block (Wq | Wk | Wv rows) of the CTA's head group
+  uint8_t* sRef = sW + 96 * 128;      // 2 x [16 x 128 B]: K rows of the reference keys (second chunks stay zero)
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform role index
   if (tid == 0) s_go = (status[0] == 0 && status[1] == 0);
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
     mbar_init(&bars[A3Bars::W], 1);
     mbar_init(&bars[A3Bars::QKV], 1);
     mbar_init(&bars[A3Bars::ACC], 4);
+    mbar_init(&bars[A3Bars::KQ], 4);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bars[A3Bars::X + b], 1);
       mbar_init(&bars[A3Bars::KV + b], 4);
@@ -111,6 +114,7 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
   //   K rows : second chunk = (1, pad_j, 0 x 6)
   //   V^T    : row 8 of every head = ones for the 250 real keys (softmax denominator), rows 9..15 = 0
   for (int i = tid; i < 2 * kA3Unit / 16; i += kAttn3Threads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < 2 * kA3RefBytes / 16; i += kAttn3Threads) reinterpret_cast<uint4*>(sRef)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
   for (int i = tid; i < 2 * 256 * 4; i += kAttn3Threads) {  // (buffer, row, head)
     const int b = i >> 10, row = (i >> 2) & 255, hh = i & 3;
@@ -205,9 +209,12 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
     for (int it = 0; it < n_it; ++it) {
       if (lds_u32(abort_a)) break;
       uint8_t* ub = smem + (it & 1) * kA3Unit;
-#pragma unroll 1
+      uint8_t* krow = ub + 2 * kSlab;
+      uint8_t* kref = sRef + (it & 1) * kA3RefBytes;
+      float md[2][4];   // the rows' own (diagonal) scores, fp32
+#pragma unroll
       for (int tile = 0; tile < 2; ++tile) {
-        const uint32_t n = 2u * (uint32_t)it + (uint32_t)tile;
+        const uint32_t n = 4u * (uint32_t)it + (uint32_t)tile;
         A3PH(1);
         wait_a(BAR(A3Bars::QKV), n & 1u, kErrAttS);
         A3PH(0);
@@ -217,8 +224,8 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
         tmem_ld_32x32(lane_addr + 32, rk);
         tmem_wait_ld();
         const int t = tile * 128 + r;      // key index inside the chunk
+        const bool is_ref = (t & 15) == 8;  // keys 8, 24, .., 248: the reference keys (one per k-mer position, roughly)
         uint8_t* qrow = ub + tile * kSlab;
-        uint8_t* krow = ub + 2 * kSlab;
 #pragma unroll
         for (int hh = 0; hh < 4; ++hh) {
           uint32_t pq[4], pk[4];
@@ -232,16 +239,16 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
             pk[i] = pack_half2(k0, k1);
             m = fmaf(q0, k0, fmaf(q1, k1, m));
           }
+          md[tile][hh] = m;
           *reinterpret_cast<uint4*>(qrow + sw128_offset(r, 2 * hh)) = make_uint4(pq[0], pq[1], pq[2], pq[3]);
-          // (-m_i, -30000): the reference of the row, subtracted by the S MMA through the ones column of K
-          *reinterpret_cast<uint4*>(qrow + sw128_offset(r, 2 * hh + 1)) = make_uint4(pack_half2(-m, -30000.0f), 0u, 0u, 0u);
           *reinterpret_cast<uint4*>(krow + sw128_offset(t, 2 * hh)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          if (is_ref) *reinterpret_cast<uint4*>(kref + sw128_offset(t >> 4, 2 * hh)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
         uint32_t rv[32];   // V after Q / K: 64 + 32 live accumulator registers instead of 96
         tmem_ld_32x32(lane_addr + 64, rv);
         tmem_wait_ld();
         tcgen05_fence_before();
-        warp_arrive_a(BAR(A3Bars::ACC));   // the accumulator may be overwritten by the next tile's projection
+        warp_arrive_a(BAR(A3Bars::ACC));   // the accumulator may be overwritten (next tile's projection / reference scores)
         uint8_t* vslab = ub + 4 * kSlab + (t >> 6) * 8192 + (t & 7) * 2;
         const uint32_t ck = (t & 63) >> 3;
 #pragma unroll
@@ -249,6 +256,38 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
 #pragma unroll
           for (int d = 0; d < 8; ++d)
             *reinterpret_cast<__half*>(vslab + sw128_offset(hh * 16 + d, ck)) = __float2half_rn(__uint_as_float(rv[8 * hh + d]));
+      }
+      // The softmax reference of a row: max of its own score and of its scores against the 16 reference keys, the latter
+      // by the tensor core ([128 x 16] per (tile, head), issued by the load warp into the projection accumulator's
+      // columns once Q and the reference keys are in shared memory).  Any reference is exact for the softmax; it only
+      // has to be close enough to the row maximum that no probability overflows fp16 (2^16).  The diagonal alone is a poor
+      // guess: with W_q, W_k scaled x3 every unit had a row whose maximum beat its own score by more than 11 nats.
+      fence_proxy_async_smem();
+      warp_arrive_a(BAR(A3Bars::KQ));
+#pragma unroll
+      for (int tile = 0; tile < 2; ++tile) {
+        const uint32_t n = 4u * (uint32_t)it + 2u + (uint32_t)tile;
+        wait_a(BAR(A3Bars::QKV), n & 1u, kErrAttS);
+        tcgen05_fence_after();
+        uint32_t rs[32], rt[32];
+        tmem_ld_32x32(lane_addr, rs);        // heads 0, 1: 16 reference scores each
+        tmem_ld_32x32(lane_addr + 32, rt);   // heads 2, 3
+        tmem_wait_ld();
+        tcgen05_fence_before();
+        warp_arrive_a(BAR(A3Bars::ACC));
+        uint8_t* qrow = ub + tile * kSlab;
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+          float m = md[tile][hh];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const uint32_t a = hh < 2 ? rs[16 * hh + j] : rt[16 * (hh - 2) + j];
+            const uint32_t b2 = hh < 2 ? rs[16 * hh + j + 1] : rt[16 * (hh - 2) + j + 1];
+            m = max3(m, __uint_as_float(a), __uint_as_float(b2));
+          }
+          // (-m_i, -30000): subtracted by the S MMA through the ones column of K; pad keys get -30000 on top
+          *reinterpret_cast<uint4*>(qrow + sw128_offset(r, 2 * hh + 1)) = make_uint4(pack_half2(-m, -30000.0f), 0u, 0u, 0u);
+        }
       }
       fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
       warp_arrive_a(BAR(A3Bars::KV + (it & 1)));
@@ -374,6 +413,8 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
       const uint32_t idesc_qkv = umma_idesc(128, 96, kFmtF16);
       const uint64_t d0 = umma_desc_k_sw128(smem_u32(smem));
       const uint64_t dW = umma_desc_k_sw128(smem_u32(sW));
+      const uint64_t dRef = umma_desc_k_sw128(smem_u32(sRef));
+      const uint32_t idesc_ref = umma_idesc(128, 16, kFmtF16);
       if (n_it > 0 && elect_one()) {
         mbar_arrive_expect_tx(&bars[A3Bars::W], 96 * 128);
         tma_load_2d(sW, &tmWg, &bars[A3Bars::W], 0, g * 96);
@@ -396,17 +437,30 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
         wait_a(BAR(A3Bars::X + buf), ((uint32_t)it >> 1) & 1u, kErrAttLoad);
         tcgen05_fence_after();
         const uint64_t dX = d0 + (uint64_t)((buf * kA3Unit) >> 4);
+        // Four accumulator uses per unit, handed over through the same two barriers (QKV: written, ACC: read):
+        // projection of tile 0, of tile 1, reference scores of tile 0, of tile 1.
 #pragma unroll
-        for (int tile = 0; tile < 2; ++tile) {
-          const uint32_t n = 2u * (uint32_t)it + (uint32_t)tile;
-          if (n >= 1u) {   // the producer has read the previous tile's accumulator
+        for (int step = 0; step < 4; ++step) {
+          const uint32_t n = 4u * (uint32_t)it + (uint32_t)step;
+          if (n >= 1u) {   // the producer has read the previous contents of the accumulator columns
             wait_a(BAR(A3Bars::ACC), (n - 1u) & 1u, kErrAttLoad);
             tcgen05_fence_after();
           }
-          if (elect_one()) {   // [128 x 96] = X_tile Wg^T
+          if (step == 2) {   // Q (without the reference) and the reference keys of the unit are in shared memory
+            wait_a(BAR(A3Bars::KQ), (uint32_t)it & 1u, kErrAttLoad);
+            tcgen05_fence_after();
+          }
+          if (elect_one()) {
+            if (step < 2) {   // [128 x 96] = X_tile Wg^T
 #pragma unroll
-            for (int s = 0; s < 4; ++s)
-              umma_f16_ss(kA3QkvCol, dX + (uint64_t)((tile * kSlab + s * 32) >> 4), dW + (uint64_t)((s * 32) >> 4), idesc_qkv, s > 0);
+              for (int s = 0; s < 4; ++s)
+                umma_f16_ss(kA3QkvCol, dX + (uint64_t)((step * kSlab + s * 32) >> 4), dW + (uint64_t)((s * 32) >> 4), idesc_qkv, s > 0);
+            } else {          // [128 x 16] = c Q_h Kref_h^T per head: the reference scores of tile (step - 2)
+#pragma unroll
+              for (int hh = 0; hh < 4; ++hh)
+                umma_f16_ss(kA3QkvCol + 16u * hh, dX + (uint64_t)(((step - 2) * kSlab + hh * 32) >> 4),
+                            dRef + (uint64_t)((buf * kA3RefBytes + hh * 32) >> 4), idesc_ref, 0u);
+            }
             umma_commit_a(BAR(A3Bars::QKV));
           }
           __syncwarp();

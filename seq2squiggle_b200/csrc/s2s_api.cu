@@ -162,7 +162,7 @@ struct Workspace {
   // per sub-batch
   float *emb, *xe, *qkv_e, *att_e, *ye, *he, *h3, *sigma;
   int32_t *dur, *total, *kidx;
-  float *xd, *qkv_d, *att_d, *yd, *hd, *sigma_ext, *p_rows;
+  float *xd, *qkv_d, *att_d, *yd, *hd, *sigma_ext;
   TcBuffers tcb;
 };
 
@@ -194,7 +194,6 @@ int64_t carve(Workspace& w, void* base, const s2s_engine* h, int64_t n_chunks, i
   w.yd = cv.take<float>(md32 * 64);
   w.hd = cv.take<float>(md32 * 256);
   w.sigma_ext = cv.take<float>(bc * S2S_L_DEC);
-  w.p_rows = cv.take<float>(md);
   tc_carve(w.tcb, cv.base, cv.off, bc);
   (void)n_reads;
   return cv.off;
@@ -218,12 +217,17 @@ int fft_block_f32(const BlockDev& b, float* x, float* y, float* qkv, float* att,
 }
 
 // The whole path for chunks [0, n_chunks): writes pA rows into pa_out[n_chunks*250].
+// counts (optional, tensor-core path): per-chunk non-zero sample counts for the compaction, written by the fused decoder
+// epilogue; *counts_done tells the caller whether they were.
 int run_pipeline(s2s_engine* h, const uint8_t* bases, const int8_t* codes, const Workspace& w, int64_t n_chunks,
-                 const s2s_run_opts& opts, float* pa_out, const s2s_taps* taps, cudaStream_t st) {
+                 const s2s_run_opts& opts, float* pa_out, const s2s_taps* taps, cudaStream_t st,
+                 int32_t* counts = nullptr, bool* counts_done = nullptr) {
   const DevWeights& dw = h->dw;
   const int k = h->cfg.seq_kmer;
   const bool tc_path = opts.precision == S2S_PREC_FP16_TC;
   const int64_t step = tc_path ? h->batch_chunks : (h->batch_chunks_f32 < h->batch_chunks ? h->batch_chunks_f32 : h->batch_chunks);
+  if (counts_done) *counts_done = tc_path && counts != nullptr;
+  if (tc_path && counts && n_chunks > 0) S2S_CUDA_OK(cudaMemsetAsync(counts, 0, (size_t)n_chunks * sizeof(int32_t), st));
   for (int64_t c0 = 0; c0 < n_chunks; c0 += step) {
     const int64_t bc = (n_chunks - c0) < step ? (n_chunks - c0) : step;
     const int64_t me = bc * S2S_L_ENC;
@@ -233,6 +237,7 @@ int run_pipeline(s2s_engine* h, const uint8_t* bases, const int8_t* codes, const
     // that contains a k-mer outside the table, and recompute that whole sub-batch with identical arithmetic
     const bool use_tab = h->tab.emb != nullptr;
     const int* run_if = use_tab ? h->tab.flag : nullptr;
+    cudaEvent_t pe = prof_begin(h->tc, st);
     if (use_tab) {
       S2S_CUDA_OK(cudaMemsetAsync(h->tab.flag, 0, sizeof(int), st));
       if (launch_embed_lookup(dw, h->tab, bases, bases ? w.chunk_base + c0 : nullptr, bases ? w.chunk_nk + c0 : nullptr,
@@ -243,6 +248,8 @@ int run_pipeline(s2s_engine* h, const uint8_t* bases, const int8_t* codes, const
                      codes ? codes + c0 * S2S_L_ENC * k : nullptr, bc, w.emb, w.xe, tc_path ? w.tcb.xe16 : nullptr, st,
                      run_if))
       return -1;
+    prof_end(h->tc, PROF_FRONT, pe, bc, st);
+    pe = prof_begin(h->tc, st);
     // encoder (modules.py:82-87)
     if (tc_path) {
       if (tc_encoder(h->tc, dw, w.tcb, w.xe, w.tcb.xe16, w.qkv_e, w.tcb.oe16, bc, st)) return -1;
@@ -250,6 +257,7 @@ int run_pipeline(s2s_engine* h, const uint8_t* bases, const int8_t* codes, const
       for (int l = 0; l < h->cfg.encoder_layers; ++l)
         if (fft_block_f32(dw.enc[l], w.xe, w.ye, w.qkv_e, w.att_e, w.he, bc, S2S_L_ENC, S2S_L_ENC, st)) return -1;
     }
+    prof_end(h->tc, PROF_ENCODER, pe, bc, st);
     // samplers (K-C)
     float* conc_tap = taps && taps->conc_dev ? taps->conc_dev + c0 * 16 : nullptr;
     float* rate_tap = taps && taps->rate_dev ? taps->rate_dev + c0 * 16 : nullptr;
@@ -261,9 +269,11 @@ int run_pipeline(s2s_engine* h, const uint8_t* bases, const int8_t* codes, const
     if (launch_sampler_heads(dw, w.h3, me, o, w.sigma, w.dur, conc_tap, rate_tap, durf_tap, st, run_if)) return -1;
     // K-D
     // fp32 path: fp32 residual stream xd; tensor-core path: the fp16 stream x16 is the only copy
+    pe = prof_begin(h->tc, st);
     if (launch_length_regulate(w.xe, w.sigma, w.dur, bc, dw.dec_pos, tc_path ? nullptr : w.xd, tc_path ? w.tcb.x16 : nullptr, S2S_L_DEC_PAD,
                                w.sigma_ext, w.total,
                                taps && taps->lr_out_dev ? taps->lr_out_dev + c0 * S2S_L_DEC * 64 : nullptr, st)) return -1;
+    prof_end(h->tc, PROF_LR, pe, bc, st);
     if (taps) {
       if (tap_copy(taps->emb_out_dev ? taps->emb_out_dev + c0 * 16 * 64 : nullptr, w.emb, me * 64 * 4, st)) return -1;
       if (tap_copy(taps->enc_out_dev ? taps->enc_out_dev + c0 * 16 * 64 : nullptr, w.xe, me * 64 * 4, st)) return -1;
@@ -273,19 +283,18 @@ int run_pipeline(s2s_engine* h, const uint8_t* bases, const int8_t* codes, const
                    bc * S2S_L_DEC * 4, st)) return -1;
     }
     // decoder (modules.py:138-139)
+    // decoder + K-F.  Tensor-core path: out_linear, x165, noise, clamp and the non-zero count live in the last FFN kernel.
+    float* pa_b = pa_out + c0 * S2S_L_DEC;
+    float* p_tap = taps && taps->p_dev ? taps->p_dev + c0 * S2S_L_DEC : nullptr;
     if (opts.precision == S2S_PREC_FP32) {
       for (int l = 0; l < h->cfg.decoder_layers; ++l)
         if (fft_block_f32(dw.dec[l], w.xd, w.yd, w.qkv_d, w.att_d, w.hd, bc, S2S_L_DEC, S2S_L_DEC_PAD, st)) return -1;
+      if (launch_out_epilogue(dw, w.xd, w.sigma_ext, bc, o, p_tap, pa_b, st)) return -1;
     } else {
-      if (tc_decoder(h->tc, dw, w.tcb, w.p_rows, bc, st)) return -1;
-    }
-    // K-F
-    float* pa_b = pa_out + c0 * S2S_L_DEC;
-    float* p_tap = taps && taps->p_dev ? taps->p_dev + c0 * S2S_L_DEC : nullptr;
-    if (tc_path) {
-      if (launch_noise_epilogue(dw, w.p_rows, w.sigma_ext, bc, o, p_tap, pa_b, st)) return -1;
-    } else if (launch_out_epilogue(dw, w.xd, w.sigma_ext, bc, o, p_tap, pa_b, st)) {
-      return -1;
+      OutEpi epi;
+      epi.pa = pa_b; epi.p_tap = p_tap; epi.sigma_ext = w.sigma_ext; epi.counts = counts ? counts + c0 : nullptr;
+      epi.scaling = dw.cfg.scaling_max_value; epi.o = o;
+      if (tc_decoder(h->tc, dw, w.tcb, epi, bc, st)) return -1;
     }
     if (taps && tap_copy(taps->pa_dev ? taps->pa_dev + c0 * S2S_L_DEC : nullptr, pa_b, bc * S2S_L_DEC * 4, st)) return -1;
   }
@@ -494,9 +503,14 @@ int s2s_forward_reads(s2s_handle h, const uint8_t* bases_dev, const int64_t* rea
   }
   if (launch_chunk_map(read_offsets_dev, chunk_offsets_dev, n_reads, n_chunks, h->cfg.seq_kmer, w.chunk_read,
                        w.chunk_base, w.chunk_nk, st)) return -1;
-  if (run_pipeline(h, bases_dev, nullptr, w, n_chunks, *opts, w.pa, taps, st)) return -1;
-  return launch_compact(w.pa, chunk_offsets_dev, n_reads, n_chunks, opts->digitisation, opts->range, opts->offset_mean,
-                        opts->rna_reverse, w.compact_ws, w.compact_bytes, raw_out_dev, raw_offsets_dev, st);
+  bool counted = false;
+  if (run_pipeline(h, bases_dev, nullptr, w, n_chunks, *opts, w.pa, taps, st, compact_counts(w.compact_ws), &counted)) return -1;
+  cudaEvent_t pe = prof_begin(h->tc, st);
+  const int rc = launch_compact(w.pa, chunk_offsets_dev, n_reads, n_chunks, opts->digitisation, opts->range,
+                                opts->offset_mean, opts->rna_reverse, w.compact_ws, w.compact_bytes, raw_out_dev,
+                                raw_offsets_dev, st, counted);
+  prof_end(h->tc, PROF_COMPACT, pe, n_chunks, st);
+  return rc;
 }
 
 int s2s_forward_chunks(s2s_handle h, const int8_t* codes_dev, int64_t n_chunks, const s2s_run_opts* opts,
@@ -529,6 +543,15 @@ int s2s_check(s2s_handle h, s2s_stream stream) {
 int s2s_profile_kernel(s2s_handle h, int enable, double* ms_total, int64_t* launches, int64_t* chunks) {
   if (!h) { set_error("null handle"); return -1; }
   return tc_profile(h->tc, enable, ms_total, launches, chunks);
+}
+
+int s2s_profile_kernel_group(s2s_handle h, const char* group, double* ms_total, int64_t* launches, int64_t* chunks) {
+  if (!h || !group) { set_error("null argument"); return -1; }
+  static const char* names[PROF_KINDS] = {"attention", "ffn", "length_regulate", "compact", "encoder", "front_end"};
+  for (int k = 0; k < PROF_KINDS; ++k)
+    if (!strcmp(group, names[k])) return tc_profile_kind(h->tc, k, ms_total, launches, chunks);
+  set_error("unknown kernel group '%s'", group);
+  return -1;
 }
 
 int s2s_debug_counters(int64_t* out, int32_t n, int32_t reset) {

@@ -104,13 +104,22 @@ int launch_length_regulate(const float* enc_out, const float* sigma, const int32
 // p = ReLU(y . w_out + b); pA = clamp(165 p + noise, 0).  y has 256 rows per chunk, outputs 250 per chunk.
 int launch_out_epilogue(const DevWeights& w, const float* y, const float* sigma_ext, int64_t n_chunks,
                         const s2s_run_opts& o, float* p_tap, float* pa, cudaStream_t st);
-// same, for p already computed per row (256 rows per chunk) by the last tensor-core FFN kernel
-int launch_noise_epilogue(const DevWeights& w, const float* p_rows, const float* sigma_ext, int64_t n_chunks,
-                          const s2s_run_opts& o, float* p_tap, float* pa, cudaStream_t st);
+// Arguments of the fused output epilogue of the last tensor-core FFN kernel (model.py:221-240 inside k_tc_fc_ffn):
+// pA = clamp(165 p + noise, 0) written once, 250 floats per chunk, plus the chunk's number of non-zero samples.
+struct OutEpi {
+  float* pa;                 // [chunks][250]
+  float* p_tap;              // optional: p = ReLU(out_linear(.)) per position
+  const float* sigma_ext;    // [chunks][250] expanded noise std
+  int32_t* counts;           // optional: per-chunk non-zero count (zeroed by the caller), input of the compaction
+  float scaling;             // scaling_max_value (165)
+  s2s_run_opts o;            // noise mode / std / seed; chunk_id_base = global index of the sub-batch's first chunk
+};
 int launch_digitise(const float* pa, int64_t n, float dig, float range, float offset, int16_t* raw, cudaStream_t st);
 int64_t compact_workspace_bytes(int64_t n_chunks);
+// counts_ready: the per-chunk non-zero counts (compact_counts(ws)) were already written by the fused decoder epilogue
 int launch_compact(const float* pa, const int64_t* chunk_offsets, int64_t n_reads, int64_t n_chunks, float dig,
                    float range, float offset, int rna_reverse, void* ws, int64_t ws_bytes, int16_t* raw,
-                   int64_t* raw_offsets, cudaStream_t st);
+                   int64_t* raw_offsets, cudaStream_t st, bool counts_ready = false);
+inline int32_t* compact_counts(void* ws) { return static_cast<int32_t*>(ws); }   // first region of the workspace
 
 }  // namespace s2s

@@ -245,6 +245,7 @@ class _ReadPipeline:
         self.stats = dict(reads=0, chunks=0, samples=0, h2d_bytes=0, d2h_bytes=0, allocs=0)
         self.trace: list = []        # S2S_PIPE_TRACE=1: per-piece host timestamps and device events (developer aid)
         self.free_slots: "queue.Queue" = queue.Queue()
+        self.pending: "OrderedDict" = OrderedDict()   # reads kept for a writer that can only write once (POD5)
         self.n_slots = 0
         self.thread: Optional[threading.Thread] = None
 
@@ -344,12 +345,19 @@ class _ReadPipeline:
             if b is None:
                 return
             try:
+                if self.err is not None:    # an earlier piece failed: writing on would leave a gap in the output
+                    continue
                 b["sig_ev"].synchronize()
                 off = b["off_host"].numpy()
                 sig = b["slot"].sig.numpy()
                 w = self.m.out_writer
                 if w is not None and hasattr(w, "save_flat"):
                     w.save_flat(b["names"], sig, off)      # one contiguous buffer + offsets: no per-read Python work
+                elif w is not None and not getattr(w, "appendable", True):
+                    # a writer that cannot append (POD5: inference.py:71-79 sets export_every_n_samples = inf, all reads
+                    # are kept and written once at on_predict_epoch_end): keep copies, the staging slot is recycled
+                    for i, name in enumerate(b["names"]):
+                        self.pending[name] = sig[off[i]:off[i + 1]].copy()
                 elif w is not None:    # the views are valid until save() returns (writer plug-point contract)
                     w.signals = OrderedDict((name, sig[off[i]:off[i + 1]]) for i, name in enumerate(b["names"]))
                     w.save()
@@ -366,6 +374,11 @@ class _ReadPipeline:
         if self.thread is not None and self.thread.is_alive():
             self.q.put(None)
             self.thread.join()
+        if self.pending and self.err is None:
+            w = self.m.out_writer
+            w.signals, self.pending = self.pending, OrderedDict()
+            w.save()
+            w.signals = []
         self.eng.check()
         if self.err:
             err, self.err = self.err, None

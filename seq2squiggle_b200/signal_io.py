@@ -252,6 +252,7 @@ class BLOW5Writer(_WriterBase):
 
 class POD5Writer(_WriterBase):
     """Export signal predictions to a pod5 file (signal_io.py:175-282).  Needs the third-party ``pod5`` package."""
+    appendable = False   # pod5.Writer refuses an existing file: the read pipeline keeps every read and saves once
 
     def save(self):
         if self.signals is None:

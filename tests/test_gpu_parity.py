@@ -246,6 +246,48 @@ def test_duration_sampler_distribution(golden_dir):
     assert not torch.equal(t3["dur_int"], t2["dur_int"])
 
 
+def test_normal_dwell_branch_distribution(golden_dir):
+    """modules.py:419-432 (duration sampler off, dwell_std > 0): dwell = normal(dwell_mean, dwell_std).clamp(min_length),
+    then round-half-even.  Our Philox Box-Muller draws against the oracle's torch.normal draws of the same branch
+    (oracle.durations_forward): two-sample KS on the float dwell, exact agreement of the clamp mass and of the rounding
+    rule, mean / std of the unclamped part within 4 standard errors."""
+    fx = np.load(os.path.join(golden_dir, "samplers_k9.npz"))
+    eng, sd, cfg = _engine(golden_dir, "ckpt_k9_seed1.ckpt")
+    codes = torch.from_numpy(fx["codes"][:8]).cuda().repeat(1000, 1, 1).contiguous()   # 8000 chunks x 16 k-mers
+    for dwell_mean, dwell_std, min_d in ((12.5, 4.0, 3), (9.0, 5.0, 3), (12.5, 0.5, 1)):
+        opts = _opts("dna-r10-prom", "fp32", dwell_mean=dwell_mean, dwell_std=dwell_std, min_duration=min_d, seed=1234)
+        _, taps = eng.forward_chunks(codes, opts, taps=["dur_float", "dur_int"])
+        d = taps["dur_float"].cpu().numpy().reshape(-1)
+        di = taps["dur_int"].cpu().numpy().reshape(-1)
+        g = torch.Generator().manual_seed(99)
+        ref_f, ref_i = orc.durations_forward(sd, torch.zeros(8000, 16, 64), dwell_mean=dwell_mean, dwell_std=dwell_std,
+                                             duration_sampling=False, min_length=min_d, generator=g)
+        ref_f, ref_i = ref_f.numpy().reshape(-1), ref_i.numpy().reshape(-1)
+        assert d.min() >= min_d and np.array_equal(di, np.rint(d).astype(np.int32))     # clamp, then half-to-even
+        assert np.array_equal(ref_i, np.rint(ref_f).astype(np.int32))
+        ks = _ks_2samp(d, ref_f)
+        assert ks.pvalue > 1e-3, (dwell_mean, dwell_std, ks)
+        # the clamped mass P(x <= min_d) and the moments of the free part, against the analytic normal
+        from math import erf, sqrt
+        p_clamp = 0.5 * (1 + erf((min_d - dwell_mean) / (dwell_std * sqrt(2))))
+        n = d.size
+        assert abs((d == min_d).mean() - p_clamp) <= 4 * sqrt(max(p_clamp * (1 - p_clamp), 1e-9) / n) + 1e-6
+        assert abs(d.mean() - ref_f.mean()) <= 4 * sqrt(2) * dwell_std / sqrt(n)
+        # a dwell histogram on the integer grid: chi-square-like bound against the oracle's histogram
+        hi = int(max(di.max(), ref_i.max())) + 1
+        h1, h2 = np.bincount(di, minlength=hi).astype(np.float64), np.bincount(ref_i, minlength=hi).astype(np.float64)
+        big = (h1 + h2) >= 40
+        z = (h1[big] - h2[big]) / np.sqrt(h1[big] + h2[big])
+        assert np.abs(z).max() < 5.0, z
+    # same seed -> identical, different seed -> different; independent of the batch split (Philox keyed by chunk id)
+    o1 = _opts("dna-r10-prom", "fp32", dwell_mean=12.5, dwell_std=4.0, seed=5)
+    _, a = eng.forward_chunks(codes[:64].contiguous(), o1, taps=["dur_int"])
+    _, b = eng.forward_chunks(codes[:64].contiguous(), o1, taps=["dur_int"])
+    _, c = eng.forward_chunks(codes[:64].contiguous(), _opts("dna-r10-prom", "fp32", dwell_mean=12.5, dwell_std=4.0, seed=6),
+                              taps=["dur_int"])
+    assert torch.equal(a["dur_int"], b["dur_int"]) and not torch.equal(a["dur_int"], c["dur_int"])
+
+
 def test_noise_amplitude_distribution(golden_dir):
     """model.py:224-240: noise only where pA != 0, sd = clamp(sigma_ext,min_noise)*noise_std*165 (sampler) or
     noise_std (static); clamp >= 0.  (pA_noisy - pA_clean)/sd must be N(0,1) where the clamp is inactive."""
@@ -406,7 +448,7 @@ def test_attention_overflow_falls_back_to_exact_kernel(golden_dir, scale):
     """The pipelined attention kernel uses one reference maximum per row (max of its first 32 scores) and flags a
     (chunk, head group) whose fp16 probabilities overflowed; the exact two-pass kernel recomputes the flagged units.
     Scaling W_q/W_k of the decoder makes scores differ by far more than the fp16 range allows, so the fallback must
-    trigger, and the result must equal the exact kernel run on its own (S2S_ATTN_V1=1)."""
+    trigger, and the result must equal the exact kernel run on its own (S2S_ATTN_EXACT=1)."""
     import ctypes as C
     from seq2squiggle_b200 import _lib
     from seq2squiggle_b200.engine import Engine
@@ -431,11 +473,11 @@ def test_attention_overflow_falls_back_to_exact_kernel(golden_dir, scale):
         for _ in range(2):
             again, _ = fast.forward_chunks(codes, opts)
             assert torch.equal(again, pa_fast)
-    os.environ["S2S_ATTN_V1"] = "1"
+    os.environ["S2S_ATTN_EXACT"] = "1"
     try:
         exact = Engine(sd, cfg, device=0)
     finally:
-        del os.environ["S2S_ATTN_V1"]
+        del os.environ["S2S_ATTN_EXACT"]
     pa_exact, _ = exact.forward_chunks(codes, opts)
     a, b = pa_fast.cpu().numpy(), pa_exact.cpu().numpy()
     if scale >= 9.0:

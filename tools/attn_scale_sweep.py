@@ -2,7 +2,7 @@
 """Developer tool: robustness of the pipelined attention against sharp attention.  W_q / W_k of the decoder layers of
 the random-init checkpoint are multiplied by `scale` (scores grow with scale^2); reports throughput and the fraction of
 (chunk, head group) units that the fast kernel flagged and the exact kernel recomputed.
-  gpurun -- python tools/attn_scale_sweep.py            (and with S2S_ATTN_BOUND=1 for the bound-reference variant)"""
+  gpurun -- python tools/attn_scale_sweep.py"""
 import ctypes as C
 import os
 import sys
@@ -23,7 +23,7 @@ b, ro, co = Engine.pack_reads(synth_reads(int(os.environ.get("READS", 2000)), se
 dev = [t.cuda() for t in (b, ro, co)]
 nr, nc = ro.numel() - 1, int(co[-1])
 counters = (C.c_int64 * 16)()
-print(f"variant: {'bound reference (S2S_ATTN_BOUND=1)' if os.environ.get('S2S_ATTN_BOUND') == '1' else 'first-32-scores reference (shipped)'}; {nc} chunks")
+print(f"k_tc_attn3 (reference = the row's own score); {nc} chunks")
 for scale in (1.0, 2.0, 3.0, 4.0, 6.0, 9.0):
     sd = dict(base)
     for layer in range(cfg["decoder_layers"]):
@@ -45,5 +45,5 @@ for scale in (1.0, 2.0, 3.0, 4.0, 6.0, 9.0):
     lib.s2s_debug_counters(counters, 16, 1)
     ms = e0.elapsed_time(e1)
     units = 2 * nc * cfg["decoder_layers"]
-    print(f"scale {scale:4.1f}: {nc / ms / 1e3:6.3f} M chunks/s, flagged units {counters[12]:8d} of {units} ({100 * counters[12] / units:5.1f} %)")
+    print(f"scale {scale:4.1f}: {nc / ms / 1e3:6.3f} M chunks/s, flagging warps {counters[12]:8d} of {4 * units} ({100 * counters[12] / (4 * units):5.1f} %)")
     eng.close()
