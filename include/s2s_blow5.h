@@ -45,6 +45,18 @@ int s2s_blow5_write_batch(s2s_blow5_handle h, int64_t n_reads, const char* read_
                           const int32_t* read_number, const uint64_t* start_time, double digitisation, double range,
                           double sampling_rate, int32_t n_threads);
 
+/* The same bytes WITHOUT a file: the file header, and the records of a batch (what s2s_blow5_write_batch appends), into a
+ * malloc'ed buffer the caller releases with s2s_blow5_free.  Multi-GPU predict (one process per GPU) writes one shared
+ * file this way: every rank encodes its batches and pwrite()s them at the offsets the ranks hand each other in read order,
+ * so there are no part files to splice afterwards (inference.py; the reference has no sharded predict). */
+int s2s_blow5_header(int format, int record_compression, const char* header_attrs, char** out, int64_t* out_bytes);
+int s2s_blow5_encode_batch(int format, int record_compression, int64_t n_reads, const char* read_ids,
+                           const int16_t* signal, const int64_t* sig_offsets, const double* offset,
+                           const double* median_before, const int32_t* read_number, const uint64_t* start_time,
+                           double digitisation, double range, double sampling_rate, int32_t n_threads, char** out,
+                           int64_t* out_bytes);
+void s2s_blow5_free(char* buf);
+
 /* Bytes written so far (header + records). */
 int64_t s2s_blow5_bytes_written(s2s_blow5_handle h);
 

@@ -44,7 +44,7 @@ class S2STaps(C.Structure):
 BLOW5_LIB_PATH = os.path.join(HERE, "libs2s_blow5.so")
 BLOW5_SOURCE = "blow5_writer.cpp"
 EXPORTS_BLOW5 = ["s2s_blow5_last_error", "s2s_blow5_open", "s2s_blow5_write_batch", "s2s_blow5_bytes_written",
-                 "s2s_blow5_close"]
+                 "s2s_blow5_close", "s2s_blow5_header", "s2s_blow5_encode_batch", "s2s_blow5_free"]
 
 
 def needs_build() -> bool:
@@ -99,6 +99,13 @@ def load_blow5() -> C.CDLL:
     lib.s2s_blow5_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(vp)]
     lib.s2s_blow5_write_batch.restype = C.c_int
     lib.s2s_blow5_write_batch.argtypes = [vp, i64, C.c_char_p, vp, vp, vp, vp, vp, vp, f64, f64, f64, i32]
+    lib.s2s_blow5_header.restype = C.c_int
+    lib.s2s_blow5_header.argtypes = [C.c_int, C.c_int, C.c_char_p, C.POINTER(vp), C.POINTER(i64)]
+    lib.s2s_blow5_encode_batch.restype = C.c_int
+    lib.s2s_blow5_encode_batch.argtypes = [C.c_int, C.c_int, i64, C.c_char_p, vp, vp, vp, vp, vp, vp, f64, f64, f64, i32,
+                                           C.POINTER(vp), C.POINTER(i64)]
+    lib.s2s_blow5_free.restype = None
+    lib.s2s_blow5_free.argtypes = [vp]
     lib.s2s_blow5_bytes_written.restype = i64
     lib.s2s_blow5_bytes_written.argtypes = [vp]
     lib.s2s_blow5_close.restype = C.c_int

@@ -84,6 +84,145 @@ struct s2s_blow5_writer {
   int64_t bytes = 0;
 };
 
+namespace {
+
+std::string header_bytes(int format, int compression, const char* header_attrs) {
+  const std::string attrs = sorted_attrs(header_attrs);
+  std::string hdr;
+  if (format == S2S_BLOW5_BINARY) {
+    const std::string ascii = attrs + kTypes + kNames;
+    hdr.assign(64, '\0');
+    memcpy(&hdr[0], kMagic, 6);
+    memcpy(&hdr[6], kVersion, 3);
+    hdr[9] = (char)compression;
+    const uint32_t n_groups = 1;
+    memcpy(&hdr[10], &n_groups, 4);
+    hdr[14] = 0;  // signal compression: none
+    const uint32_t hsize = (uint32_t)ascii.size();
+    hdr.append(reinterpret_cast<const char*>(&hsize), 4);
+    hdr += ascii;
+  } else {
+    hdr = "#slow5_version\t0.2.0\n#num_read_groups\t1\n" + attrs + kTypes + kNames;
+  }
+  return hdr;
+}
+
+// The records of a batch, laid out (or deflated) by a pool of threads: one string per thread, in record order.
+int encode_records(int format, int compression, int64_t n_reads, const char* read_ids, const int16_t* signal,
+                   const int64_t* sig_offsets, const double* offset, const double* median_before,
+                   const int32_t* read_number, const uint64_t* start_time, double digitisation, double range,
+                   double sampling_rate, int32_t n_threads, std::vector<std::string>& chunks);
+
+}  // namespace
+
+namespace {
+
+int encode_records(int format, int compression, int64_t n_reads, const char* read_ids, const int16_t* signal,
+                   const int64_t* sig_offsets, const double* offset, const double* median_before,
+                   const int32_t* read_number, const uint64_t* start_time, double digitisation, double range,
+                   double sampling_rate, int32_t n_threads, std::vector<std::string>& chunks) {
+  if (!read_ids || !sig_offsets || !offset || !median_before || !read_number || !start_time || (!signal && sig_offsets[n_reads] > 0)) {
+    set_error("null argument");
+    return -1;
+  }
+  std::vector<const char*> ids((size_t)n_reads);
+  std::vector<uint32_t> id_len((size_t)n_reads);
+  const char* p = read_ids;
+  for (int64_t r = 0; r < n_reads; ++r) {
+    ids[r] = p;
+    size_t l = strlen(p);
+    if (l > 65535) { set_error("read id longer than 65535 bytes"); return -1; }
+    id_len[r] = (uint32_t)l;
+    p += l + 1;
+  }
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 64) n_threads = 64;
+  if ((int64_t)n_threads > n_reads) n_threads = (int32_t)n_reads;
+
+  chunks.assign((size_t)n_threads, std::string());
+  auto body_size = [&](int64_t r) -> size_t {
+    const size_t n = (size_t)(sig_offsets[r + 1] - sig_offsets[r]);
+    return 2 + id_len[r] + 4 + 32 + 8 + 2 * n + (8 + 1) + 8 + 4 + 1 + 8;
+  };
+  auto fill_body = [&](int64_t r, char* q) {
+    const uint64_t n = (uint64_t)(sig_offsets[r + 1] - sig_offsets[r]);
+    put<uint16_t>(q, (uint16_t)id_len[r]);
+    memcpy(q, ids[r], id_len[r]); q += id_len[r];
+    put<uint32_t>(q, 0u);
+    put<double>(q, digitisation); put<double>(q, offset[r]); put<double>(q, range); put<double>(q, sampling_rate);
+    put<uint64_t>(q, n);
+    memcpy(q, signal + sig_offsets[r], 2 * n); q += 2 * n;
+    put<uint64_t>(q, 1ull); *q++ = '0';           // channel_number "0"
+    put<double>(q, median_before[r]);
+    put<int32_t>(q, read_number[r]);
+    put<uint8_t>(q, 0);                           // start_mux
+    put<uint64_t>(q, start_time[r]);
+  };
+  std::vector<int> status((size_t)n_threads, 0);
+  auto work = [&](int t) {
+    const int64_t lo = n_reads * t / n_threads, hi = n_reads * (t + 1) / n_threads;
+    std::string& out = chunks[t];
+    if (format == S2S_SLOW5_ASCII) {
+      for (int64_t r = lo; r < hi; ++r) {
+        const int64_t n = sig_offsets[r + 1] - sig_offsets[r];
+        out.append(ids[r], id_len[r]);
+        out += "\t0\t" + fmt_double(digitisation) + "\t" + fmt_double(offset[r]) + "\t" + fmt_double(range) + "\t" +
+               fmt_double(sampling_rate) + "\t" + std::to_string(n) + "\t";
+        char num[8];
+        for (int64_t i = 0; i < n; ++i) {
+          int len = snprintf(num, sizeof num, "%d", (int)signal[sig_offsets[r] + i]);
+          if (i) out.push_back(',');
+          out.append(num, (size_t)len);
+        }
+        out += "\t0\t" + fmt_double(median_before[r]) + "\t" + std::to_string(read_number[r]) + "\t0\t" +
+               std::to_string((unsigned long long)start_time[r]) + "\n";
+      }
+      return;
+    }
+    if (compression == S2S_BLOW5_COMPRESS_NONE) {
+      size_t total = 0;
+      for (int64_t r = lo; r < hi; ++r) total += 8 + body_size(r);
+      out.resize(total);
+      char* q = &out[0];
+      for (int64_t r = lo; r < hi; ++r) {
+        const size_t bs = body_size(r);
+        put<uint64_t>(q, (uint64_t)bs);
+        fill_body(r, q);
+        q += bs;
+      }
+      return;
+    }
+    std::vector<char> body;
+    std::vector<unsigned char> comp;
+    for (int64_t r = lo; r < hi; ++r) {
+      const size_t bs = body_size(r);
+      body.resize(bs);
+      fill_body(r, body.data());
+      uLongf clen = compressBound((uLong)bs);
+      comp.resize(clen);
+      if (compress2(comp.data(), &clen, reinterpret_cast<const Bytef*>(body.data()), (uLong)bs, Z_DEFAULT_COMPRESSION) != Z_OK) {
+        status[t] = -1;
+        return;
+      }
+      const uint64_t sz = (uint64_t)clen;
+      out.append(reinterpret_cast<const char*>(&sz), 8);
+      out.append(reinterpret_cast<const char*>(comp.data()), clen);
+    }
+  };
+  if (n_threads == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t) pool.emplace_back(work, t);
+    for (auto& th : pool) th.join();
+  }
+  for (int t = 0; t < n_threads; ++t)
+    if (status[t]) { set_error("zlib compression failed"); return -1; }
+  return 0;
+}
+
+}  // namespace
+
 extern "C" {
 
 const char* s2s_blow5_last_error(void) { return g_err; }
@@ -126,23 +265,7 @@ int s2s_blow5_open(const char* path, int format, int append, int record_compress
   } else {
     w->fp = fopen(path, "wb");
     if (!w->fp) { set_error("cannot create %s", path); delete w; return -1; }
-    const std::string attrs = sorted_attrs(header_attrs);
-    std::string hdr;
-    if (format == S2S_BLOW5_BINARY) {
-      const std::string ascii = attrs + kTypes + kNames;
-      hdr.assign(64, '\0');
-      memcpy(&hdr[0], kMagic, 6);
-      memcpy(&hdr[6], kVersion, 3);
-      hdr[9] = (char)w->compression;
-      const uint32_t n_groups = 1;
-      memcpy(&hdr[10], &n_groups, 4);
-      hdr[14] = 0;  // signal compression: none
-      const uint32_t hsize = (uint32_t)ascii.size();
-      hdr.append(reinterpret_cast<const char*>(&hsize), 4);
-      hdr += ascii;
-    } else {
-      hdr = "#slow5_version\t0.2.0\n#num_read_groups\t1\n" + attrs + kTypes + kNames;
-    }
+    const std::string hdr = header_bytes(format, w->compression, header_attrs);
     if (fwrite(hdr.data(), 1, hdr.size(), w->fp) != hdr.size()) {
       set_error("short write of the header to %s", path); fclose(w->fp); delete w; return -1;
     }
@@ -158,111 +281,57 @@ int s2s_blow5_write_batch(s2s_blow5_handle h, int64_t n_reads, const char* read_
                           double sampling_rate, int32_t n_threads) {
   if (!h || !h->fp) { set_error("writer is not open"); return -1; }
   if (n_reads <= 0) return 0;
-  if (!read_ids || !sig_offsets || !offset || !median_before || !read_number || !start_time || (!signal && sig_offsets[n_reads] > 0)) {
-    set_error("null argument");
+  std::vector<std::string> chunks;
+  if (encode_records(h->format, h->compression, n_reads, read_ids, signal, sig_offsets, offset, median_before, read_number,
+                     start_time, digitisation, range, sampling_rate, n_threads, chunks))
     return -1;
-  }
-  std::vector<const char*> ids((size_t)n_reads);
-  std::vector<uint32_t> id_len((size_t)n_reads);
-  const char* p = read_ids;
-  for (int64_t r = 0; r < n_reads; ++r) {
-    ids[r] = p;
-    size_t l = strlen(p);
-    if (l > 65535) { set_error("read id longer than 65535 bytes"); return -1; }
-    id_len[r] = (uint32_t)l;
-    p += l + 1;
-  }
-  if (n_threads < 1) n_threads = 1;
-  if (n_threads > 64) n_threads = 64;
-  if ((int64_t)n_threads > n_reads) n_threads = (int32_t)n_reads;
-
-  std::vector<std::string> chunks((size_t)n_threads);
-  auto body_size = [&](int64_t r) -> size_t {
-    const size_t n = (size_t)(sig_offsets[r + 1] - sig_offsets[r]);
-    return 2 + id_len[r] + 4 + 32 + 8 + 2 * n + (8 + 1) + 8 + 4 + 1 + 8;
-  };
-  auto fill_body = [&](int64_t r, char* q) {
-    const uint64_t n = (uint64_t)(sig_offsets[r + 1] - sig_offsets[r]);
-    put<uint16_t>(q, (uint16_t)id_len[r]);
-    memcpy(q, ids[r], id_len[r]); q += id_len[r];
-    put<uint32_t>(q, 0u);
-    put<double>(q, digitisation); put<double>(q, offset[r]); put<double>(q, range); put<double>(q, sampling_rate);
-    put<uint64_t>(q, n);
-    memcpy(q, signal + sig_offsets[r], 2 * n); q += 2 * n;
-    put<uint64_t>(q, 1ull); *q++ = '0';           // channel_number "0"
-    put<double>(q, median_before[r]);
-    put<int32_t>(q, read_number[r]);
-    put<uint8_t>(q, 0);                           // start_mux
-    put<uint64_t>(q, start_time[r]);
-  };
-  std::vector<int> status((size_t)n_threads, 0);
-  auto work = [&](int t) {
-    const int64_t lo = n_reads * t / n_threads, hi = n_reads * (t + 1) / n_threads;
-    std::string& out = chunks[t];
-    if (h->format == S2S_SLOW5_ASCII) {
-      for (int64_t r = lo; r < hi; ++r) {
-        const int64_t n = sig_offsets[r + 1] - sig_offsets[r];
-        out.append(ids[r], id_len[r]);
-        out += "\t0\t" + fmt_double(digitisation) + "\t" + fmt_double(offset[r]) + "\t" + fmt_double(range) + "\t" +
-               fmt_double(sampling_rate) + "\t" + std::to_string(n) + "\t";
-        char num[8];
-        for (int64_t i = 0; i < n; ++i) {
-          int len = snprintf(num, sizeof num, "%d", (int)signal[sig_offsets[r] + i]);
-          if (i) out.push_back(',');
-          out.append(num, (size_t)len);
-        }
-        out += "\t0\t" + fmt_double(median_before[r]) + "\t" + std::to_string(read_number[r]) + "\t0\t" +
-               std::to_string((unsigned long long)start_time[r]) + "\n";
-      }
-      return;
-    }
-    if (h->compression == S2S_BLOW5_COMPRESS_NONE) {
-      size_t total = 0;
-      for (int64_t r = lo; r < hi; ++r) total += 8 + body_size(r);
-      out.resize(total);
-      char* q = &out[0];
-      for (int64_t r = lo; r < hi; ++r) {
-        const size_t bs = body_size(r);
-        put<uint64_t>(q, (uint64_t)bs);
-        fill_body(r, q);
-        q += bs;
-      }
-      return;
-    }
-    std::vector<char> body;
-    std::vector<unsigned char> comp;
-    for (int64_t r = lo; r < hi; ++r) {
-      const size_t bs = body_size(r);
-      body.resize(bs);
-      fill_body(r, body.data());
-      uLongf clen = compressBound((uLong)bs);
-      comp.resize(clen);
-      if (compress2(comp.data(), &clen, reinterpret_cast<const Bytef*>(body.data()), (uLong)bs, Z_DEFAULT_COMPRESSION) != Z_OK) {
-        status[t] = -1;
-        return;
-      }
-      const uint64_t sz = (uint64_t)clen;
-      out.append(reinterpret_cast<const char*>(&sz), 8);
-      out.append(reinterpret_cast<const char*>(comp.data()), clen);
-    }
-  };
-  if (n_threads == 1) {
-    work(0);
-  } else {
-    std::vector<std::thread> pool;
-    for (int t = 0; t < n_threads; ++t) pool.emplace_back(work, t);
-    for (auto& th : pool) th.join();
-  }
-  for (int t = 0; t < n_threads; ++t) {
-    if (status[t]) { set_error("zlib compression failed"); return -1; }
-    if (!chunks[t].empty() && fwrite(chunks[t].data(), 1, chunks[t].size(), h->fp) != chunks[t].size()) {
+  for (auto& c : chunks) {
+    if (!c.empty() && fwrite(c.data(), 1, c.size(), h->fp) != c.size()) {
       set_error("short write (disk full?)");
       return -1;
     }
-    h->bytes += (int64_t)chunks[t].size();
+    h->bytes += (int64_t)c.size();
   }
   return 0;
 }
+
+int s2s_blow5_header(int format, int record_compression, const char* header_attrs, char** out, int64_t* out_bytes) {
+  if (!out || !out_bytes) { set_error("null argument"); return -1; }
+  const std::string hdr = header_bytes(format, format == S2S_BLOW5_BINARY ? record_compression : S2S_BLOW5_COMPRESS_NONE,
+                                       header_attrs);
+  *out = static_cast<char*>(malloc(hdr.size() ? hdr.size() : 1));
+  if (!*out) { set_error("out of memory"); return -1; }
+  memcpy(*out, hdr.data(), hdr.size());
+  *out_bytes = (int64_t)hdr.size();
+  return 0;
+}
+
+int s2s_blow5_encode_batch(int format, int record_compression, int64_t n_reads, const char* read_ids,
+                           const int16_t* signal, const int64_t* sig_offsets, const double* offset,
+                           const double* median_before, const int32_t* read_number, const uint64_t* start_time,
+                           double digitisation, double range, double sampling_rate, int32_t n_threads, char** out,
+                           int64_t* out_bytes) {
+  if (!out || !out_bytes) { set_error("null argument"); return -1; }
+  *out = nullptr;
+  *out_bytes = 0;
+  if (n_reads <= 0) return 0;
+  std::vector<std::string> chunks;
+  if (encode_records(format, format == S2S_BLOW5_BINARY ? record_compression : S2S_BLOW5_COMPRESS_NONE, n_reads, read_ids,
+                     signal, sig_offsets, offset, median_before, read_number, start_time, digitisation, range,
+                     sampling_rate, n_threads, chunks))
+    return -1;
+  size_t total = 0;
+  for (auto& c : chunks) total += c.size();
+  char* buf = static_cast<char*>(malloc(total ? total : 1));
+  if (!buf) { set_error("out of memory (%zu bytes)", total); return -1; }
+  size_t pos = 0;
+  for (auto& c : chunks) { memcpy(buf + pos, c.data(), c.size()); pos += c.size(); }
+  *out = buf;
+  *out_bytes = (int64_t)total;
+  return 0;
+}
+
+void s2s_blow5_free(char* buf) { free(buf); }
 
 int64_t s2s_blow5_bytes_written(s2s_blow5_handle h) { return h ? h->bytes : -1; }
 

@@ -7,41 +7,43 @@ count and pushed through ``seq2squiggle.predict_reads`` (``model.py`` here), i.e
 and the file writer overlapped.
 
 Multi-GPU (``torchrun --nproc-per-node N -m seq2squiggle_b200 predict ...``): one process per GPU.  Every rank
-derives the same read list from the seed, takes a contiguous range of reads balanced by chunk count
-(``shard_reads``), keys its Philox draws by the *global* chunk index (results do not depend on N) and writes
-``<stem>.part<rank>.blow5`` with its GLOBAL read numbers / ids.  At the end rank 0's part becomes ``<out>`` and every
-other rank splices its own records into it at its byte offset, all ranks in parallel (``splice_blow5_part``: kernel
-``copy_file_range`` + a vectorised ``start_time`` shift), instead of one rank re-writing the whole output record by
-record (``merge_blow5_parts``, kept as the stand-alone tool).  No collective touches the data path; the only
-communication is one small all-gather (bytes and samples per rank) and two barriers on the gloo control plane.
+derives the same read list from the seed WITHOUT building it (a lengths-only replay of the sampler), cuts it into
+batches of about one pipeline piece (``plan_batches``), takes every N-th batch, keys its Philox draws by the *global*
+chunk index (results do not depend on N) and writes its batches' records — global read numbers / ids, ``start_time`` and
+the per-record NumPy draws of the single-process stream — straight into the ONE output file at the byte offset the owner
+of the previous batch publishes (``signal_io.SharedOrder``, a small shared table).  Encoding and ``pwrite`` of the ranks
+run in parallel and overlap the compute; there are no part files and no merge pass.  No collective touches the data
+path; the gloo control plane carries two barriers (and the random seed of ``-s 0``).
 """
 from __future__ import annotations
 
 import logging
 import os
-import struct
-from typing import Iterable, Iterator, List, Sequence, Tuple
+from typing import Optional, Iterable, Iterator, List, Sequence, Tuple
 
 import numpy as np
 
 from .checkpoint import check_model
+import itertools
+
 from .profiles import get_profile, update_config, update_profile
-from .reads import get_reads, get_reads_shard
-from .signal_io import BLOW5Writer, POD5Writer, indexed_uuid
+from .reads import get_reads, get_reads_batches
+from .signal_io import BLOW5Writer, POD5Writer
 
 logger = logging.getLogger("seq2squiggle")
 
 BATCH_CHUNKS = int(os.environ.get("S2S_READ_BATCH_CHUNKS", 131072))  # chunks per predict_reads() call
 
 
-def get_writer(out, profile, ideal_mode, export_every_n_samples, profile_name, preserve_read_ids):
-    """inference.py:28-82: writer by extension; an existing output file is deleted."""
+def get_writer(out, profile, ideal_mode, export_every_n_samples, profile_name, preserve_read_ids, remove_existing=True):
+    """inference.py:28-82: writer by extension; an existing output file is deleted (``remove_existing=False``: the
+    caller — rank 0 of a sharded run — has done that already)."""
     out = str(out)
     out_base = os.path.basename(out)
     out_dir = os.path.dirname(out)
     if out_dir and not os.path.exists(out_dir):
         os.makedirs(out_dir, exist_ok=True)
-    if os.path.exists(out):
+    if remove_existing and os.path.exists(out):
         logger.warning(f"Output file {out} already exists. File will be deleted.")
         os.remove(out)
     if any(out_base.endswith(ext) for ext in (".blow5", ".slow5")):
@@ -100,156 +102,22 @@ def shard_reads(chunk_counts: Sequence[int], world_size: int) -> List[Tuple[int,
     return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
 
 
-def merge_blow5_parts(out: str, parts: Sequence[str], preserve_read_ids: bool) -> Tuple[int, int]:
-    """Stitches uncompressed BLOW5 part files (one per rank, in rank order) into ``out``: the first part's header is
-    kept; every record's read_number / start_time (and the synthetic read id) is shifted by the totals of the
-    parts before it, which is what a single writer would have produced.  Returns (reads, samples)."""
-    reads_total = samples_total = 0
-    with open(out, "wb") as fo:
-        for pi, part in enumerate(parts):
-            with open(part, "rb") as fi:
-                head = fi.read(64)
-                if head[:6] != b"BLOW5\x01":
-                    raise ValueError(f"{part} is not a BLOW5 file")
-                if head[9] != 0:
-                    raise ValueError("merge_blow5_parts needs uncompressed records")
-                (hsize,) = struct.unpack("<I", fi.read(4))
-                ascii_hdr = fi.read(hsize)
-                if pi == 0:
-                    fo.write(head + struct.pack("<I", hsize) + ascii_hdr)
-                base_reads, base_samples = reads_total, samples_total
-                while True:
-                    szb = fi.read(8)
-                    if szb[:5] == b"5WOLB" or len(szb) < 8:
-                        break
-                    (size,) = struct.unpack("<Q", szb)
-                    body = bytearray(fi.read(size))
-                    (idl,) = struct.unpack_from("<H", body, 0)
-                    (siglen,) = struct.unpack_from("<Q", body, 2 + idl + 4 + 32)
-                    (rnum,) = struct.unpack_from("<i", body, size - 13)
-                    (stime,) = struct.unpack_from("<Q", body, size - 8)
-                    struct.pack_into("<i", body, size - 13, rnum + base_reads)
-                    struct.pack_into("<Q", body, size - 8, stime + base_samples)
-                    if not preserve_read_ids:
-                        new_id = str(indexed_uuid(rnum + base_reads + 1)).encode()
-                        if len(new_id) == idl:
-                            body[2:2 + idl] = new_id
-                    fo.write(szb)
-                    fo.write(body)
-                    reads_total = max(reads_total, rnum + base_reads + 1)
-                    samples_total += siglen
-        fo.write(b"5WOLB")
-    return reads_total, samples_total
-
-
-def blow5_record_span(path: str) -> Tuple[int, int]:
-    """``(first byte of the first record, byte after the last record)`` of an uncompressed BLOW5 file."""
-    with open(path, "rb") as f:
-        head = f.read(64)
-        if head[:6] != b"BLOW5\x01":
-            raise ValueError(f"{path} is not a BLOW5 file")
-        if head[9] != 0:
-            raise ValueError("splicing BLOW5 parts needs uncompressed records")
-        (hsize,) = struct.unpack("<I", f.read(4))
-        f.seek(0, os.SEEK_END)
-        end = f.tell()
-        f.seek(end - 5)
-        if f.read(5) != b"5WOLB":
-            raise ValueError(f"{path} has no end-of-file marker (writer not closed?)")
-    return 64 + 4 + hsize, end - 5
-
-
-def splice_blow5_part(out: str, part: str, dst_offset: int, start_time_shift: int) -> int:
-    """Copies the records of ``part`` into ``out`` at byte ``dst_offset`` and adds ``start_time_shift`` (the samples
-    written by the ranks before this one) to every record's ``start_time`` — the last eight bytes of a record, as in
-    ``merge_blow5_parts``.  Run by every rank > 0 at the same time on disjoint byte ranges of ``out``.  The bulk copy is
-    ``os.copy_file_range`` (in-kernel; falls back to read + pwrite), the shift one gather / add / scatter over a memory
-    map of the part file (which is modified).  Returns the number of records."""
-    lo, hi = blow5_record_span(part)
-    n_bytes = hi - lo
-    if n_bytes == 0:
-        return 0
-    src = os.open(part, os.O_RDONLY)
-    try:
-        ends, pos = [], lo                                   # record boundaries from the 8-byte size prefixes
-        while pos < hi:
-            (size,) = struct.unpack("<Q", os.pread(src, 8, pos))
-            pos += 8 + size
-            ends.append(pos - lo)
-    finally:
-        os.close(src)
-    if pos != hi:
-        raise ValueError(f"{part}: records do not end at the end-of-file marker")
-    if start_time_shift:     # patched in the rank's own part file, before the copy: no page of `out` is shared between ranks
-        mm = np.memmap(part, dtype=np.uint8, mode="r+", offset=lo, shape=(n_bytes,))
-        idx = (np.asarray(ends, dtype=np.int64) - 8)[:, None] + np.arange(8, dtype=np.int64)[None, :]
-        st = np.ascontiguousarray(mm[idx]).view("<u8")[:, 0] + np.uint64(start_time_shift)
-        mm[idx] = st.astype("<u8").view(np.uint8).reshape(-1, 8)
-        mm.flush()
-        del mm
-    src = os.open(part, os.O_RDONLY)
-    dst = os.open(out, os.O_RDWR)
-    try:
-        done = 0
-        use_cfr = hasattr(os, "copy_file_range")
-        while done < n_bytes:
-            want = min(n_bytes - done, 1 << 30)
-            if use_cfr:
-                try:
-                    got = os.copy_file_range(src, dst, want, lo + done, dst_offset + done)
-                    if got <= 0:
-                        raise OSError("copy_file_range copied nothing")
-                    done += got
-                    continue
-                except OSError:
-                    use_cfr = False                          # e.g. across file systems on an old kernel
-            buf = os.pread(src, min(want, 64 << 20), lo + done)
-            os.pwrite(dst, buf, dst_offset + done)
-            done += len(buf)
-    finally:
-        os.close(src)
-        os.close(dst)
-    return len(ends)
-
-
-def splice_parts_collective(out: str, my_part: str, rank: int, world: int, my_samples: int, dist) -> Tuple[int, int]:
-    """The end of a sharded run, called by every rank once its writer has closed ``my_part``: rank 0's part becomes
-    ``out`` (a rename), the others splice their records in at their byte offsets at the same time.  The parts carry
-    global read numbers / ids already (``writer._id_base`` = the shard's first read); only ``start_time``, a running sum
-    over all earlier reads of the run, needs the totals of the earlier ranks.  Returns (bytes, samples) of ``out``."""
-    lo, hi = blow5_record_span(my_part)
-    info = [None] * world
-    dist.all_gather_object(info, (hi - lo, int(my_samples), lo))
-    body = [b for b, _, _ in info]
-    samples = [n for _, n, _ in info]
-    first = info[0][2]                                       # the kept header is rank 0's
-    total = first + sum(body) + 5
-    if rank == 0:
-        os.replace(my_part, out)
-        with open(out, "r+b") as f:
-            f.truncate(total)                                # drops rank 0's end marker / reserves the other ranks' ranges
-    dist.barrier()
-    if rank > 0:
-        splice_blow5_part(out, my_part, first + sum(body[:rank]), sum(samples[:rank]))
-        os.remove(my_part)
-    dist.barrier()
-    if rank == 0:
-        with open(out, "r+b") as f:
-            f.seek(total - 5)
-            f.write(b"5WOLB")
-    return total, sum(samples)
-
-
-def part_path(out: str, rank: int) -> str:
-    """Per-rank part file of a multi-GPU run: ``sim.blow5`` -> ``sim.part<rank>.blow5`` (keeps the extension, so the
-    writer factory's extension check applies to it as to any output).  ``S2S_PART_DIR`` moves the parts of the ranks
-    > 0 to another directory — a tmpfs such as /dev/shm turns "write the part, then copy it into the output" into one
-    pass over the disk; rank 0's part stays beside ``out`` because it *becomes* the output by a rename."""
-    stem, ext = os.path.splitext(str(out))
-    part_dir = os.environ.get("S2S_PART_DIR")
-    if part_dir and rank > 0:
-        stem = os.path.join(part_dir, os.path.basename(stem))
-    return f"{stem}.part{rank}{ext}"
+def plan_batches(chunk_counts: Sequence[int], batch_chunks: Optional[int] = None) -> List[Tuple[int, int]]:
+    """Read ranges ``[lo, hi)`` of the batches of a sharded run, in read order: a batch is closed by the read that
+    brings it to ``batch_chunks`` chunks (a read is never split) — the rule of ``predict_reads``' pipeline pieces, so one
+    batch is one piece.  Batch ``b`` is simulated and written by rank ``b % world``."""
+    if batch_chunks is None:
+        from .model import PIPE_CHUNKS
+        batch_chunks = PIPE_CHUNKS
+    counts = np.asarray(chunk_counts, dtype=np.int64)
+    plan, lo = [], 0
+    cum = np.concatenate([[0], np.cumsum(counts)])
+    while lo < len(counts):
+        hi = int(np.searchsorted(cum, cum[lo] + batch_chunks, side="left"))     # first hi with sum(lo..hi-1) >= batch_chunks
+        hi = min(max(hi, lo + 1), len(counts))
+        plan.append((lo, hi))
+        lo = hi
+    return plan
 
 
 def _dist_env():
@@ -279,19 +147,17 @@ def inference_run(config: dict, saved_weights: str, fasta: str, read_input: bool
 
     rank, world, local = _dist_env()
     out = str(out)
-    my_out = out
     if world > 1:
-        if not out.endswith(".blow5"):
-            raise ValueError("multi-GPU predict writes BLOW5 part files: use a .blow5 output")
-        my_out = part_path(out, rank)
+        # Sharded run (one process per GPU, torchrun): the batches of the read list are dealt to the ranks round-robin and
+        # every rank writes its batches straight into the ONE output file, at offsets the ranks hand each other in read
+        # order (signal_io.SharedOrder) — no part files, no splice pass after the compute.
+        if not (out.endswith(".blow5") or out.endswith(".slow5")):
+            raise ValueError("multi-GPU predict writes one shared SLOW5/BLOW5 file: use a .blow5 / .slow5 output")
         if rank == 0 and os.path.exists(out):
             logger.warning(f"Output file {out} already exists. File will be deleted.")
             os.remove(out)
-    writer, export_every_n_samples = get_writer(my_out if world > 1 else out, profile_dict, ideal_mode,
-                                                export_every_n_samples, profile_name=profile,
-                                                preserve_read_ids=preserve_read_ids)
-    if world > 1:
-        writer.filename = my_out
+    writer, export_every_n_samples = get_writer(out, profile_dict, ideal_mode, export_every_n_samples, profile_name=profile,
+                                                preserve_read_ids=preserve_read_ids, remove_existing=world == 1)
     if saved_weights is None:
         saved_weights = get_saved_weights(profile)
 
@@ -308,36 +174,47 @@ def inference_run(config: dict, saved_weights: str, fasta: str, read_input: bool
     # sequential Python); a sharded multi-process run first replays the sampler for the read lengths alone to
     # balance the ranks by chunk count, then materialises only its own reads (reads.get_reads_shard)
     k = config["seq_kmer"]
-    chunk_base = 0
     if world > 1:
         import torch.distributed as dist
+        from .signal_io import SharedOrder
         if not dist.is_initialized():
-            dist.init_process_group("gloo")      # control plane only: a barrier before the merge
-        reads, (lo, hi), n_all, chunk_base = get_reads_shard(
-            fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len, rank, world, shard_reads,
+            dist.init_process_group("gloo")      # control plane only: barriers around the shared file
+        reads, plan, counts = get_reads_batches(
+            fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len, rank, world, plan_batches,
             chunks_of_read, cheap_names=not preserve_read_ids)
-        logger.info(f"rank {rank}/{world}: reads [{lo}, {hi}) of {n_all}, first global chunk {chunk_base}")
-        writer._id_base = lo                       # read_number / synthetic read ids are global from the start
-        np.random.seed((seed + rank) % (2 ** 32))  # per-record offset / median_before draws differ per rank
-    else:
-        reads, total_l = get_reads(fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len,
-                                   stream=True, cheap_names=not preserve_read_ids)
-    load_model.chunks_done = chunk_base
+        chunk_cum = np.concatenate([[0], np.cumsum(counts)])
+        mine = list(range(rank, len(plan), world))
+        logger.info(f"rank {rank}/{world}: {len(mine)} of {len(plan)} batches, {len(counts)} reads in the run")
+        order_path = out + ".order"
+        if rank == 0:
+            shared = SharedOrder(order_path, len(plan), create=True)
+        dist.barrier()
+        if rank != 0:
+            shared = SharedOrder(order_path, len(plan), create=False)
+        np.random.seed(seed % (2 ** 32))       # every rank replays the ONE per-record draw stream (offset / median_before)
+        writer.begin_shared(shared, rank)
+        n_reads = 0
+        it = iter(reads)
+        for b in mine:
+            lo, hi = plan[b]
+            batch = list(itertools.islice(it, hi - lo))
+            load_model.predict_reads(batch, chunk_id_base=int(chunk_cum[lo]), tag=(b, lo))
+            n_reads += len(batch)
+        load_model.on_predict_epoch_end()
+        writer.end_shared()
+        stats = getattr(load_model, "last_stats", None)
+        logger.info(f"rank {rank}: simulated {n_reads} reads, {writer.samples_written} samples -> {out}")
+        dist.barrier()
+        if rank == 0:
+            os.remove(order_path)
+        return stats
+    reads, total_l = get_reads(fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len,
+                               stream=True, cheap_names=not preserve_read_ids)
     n_reads = 0
     for batch in batch_reads(reads, k):
         load_model.predict_reads(batch)
         n_reads += len(batch)
     load_model.on_predict_epoch_end()
     stats = getattr(load_model, "last_stats", None)
-    logger.info(f"rank {rank}: simulated {n_reads} reads, {writer.samples_written} samples -> {writer.filename}")
-
-    if world > 1:
-        import torch.distributed as dist
-        if not os.path.exists(my_out):           # a rank without reads still contributes an (empty) part
-            writer.signals = {}
-            writer.save()
-        nbytes, ns = splice_parts_collective(out, my_out, rank, world, writer.samples_written, dist)
-        if rank == 0:
-            logger.info(f"spliced {world} parts: {ns} samples, {nbytes} bytes -> {out}")
-        dist.barrier()
+    logger.info(f"simulated {n_reads} reads, {writer.samples_written} samples -> {writer.filename}")
     return stats

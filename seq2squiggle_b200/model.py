@@ -33,7 +33,7 @@ from .signal_io import BLOW5Writer
 logger = logging.getLogger("seq2squiggle")
 
 PIPE_TRACE = bool(int(os.environ.get("S2S_PIPE_TRACE", "0")))
-PIPE_CHUNKS = 65536   # chunks per pipeline piece of predict_reads (2 engine sub-batches)
+PIPE_CHUNKS = int(os.environ.get("S2S_PIPE_CHUNKS", 65536))   # chunks per pipeline piece of predict_reads (2 engine sub-batches)
 PIPE_DEPTH = 3        # pieces the host may queue ahead of the one whose result it waits for (absorbs host jitter)
 PIPE_SLOTS = PIPE_DEPTH + 6   # pinned staging slots: PIPE_DEPTH + 1 on the device side, 4 queued for the writer, 1 in save()
 
@@ -173,9 +173,10 @@ class seq2squiggle:
     # ------------------------------------------------------------------------------------------
     # native fast path: whole reads in, int16 signals out, copies and writer overlapped with compute
     # ------------------------------------------------------------------------------------------
-    def predict_reads(self, reads: Sequence[Tuple[str, str]], chunk_id_base: Optional[int] = None):
+    def predict_reads(self, reads: Sequence[Tuple[str, str]], chunk_id_base: Optional[int] = None, tag=None):
         """``reads``: ``[(sequence, name), ...]`` (what ``get_reads`` yields).  Every read is complete, so each batch
-        is exported as soon as its signal reaches the host (no ``keep_last`` hold-back needed)."""
+        is exported as soon as its signal reaches the host (no ``keep_last`` hold-back needed).  ``tag`` (sharded runs:
+        ``(batch index, first global read)``) makes the whole call ONE pipeline piece and is handed to the writer."""
         if self._pipe is None:
             self._pipe = _ReadPipeline(self)
         # pieces of about PIPE_CHUNKS chunks: the copy / writer stages run one piece behind the compute stage, so the
@@ -186,12 +187,12 @@ class seq2squiggle:
             piece.append(item)
             nk = len(item[0]) - k + 1
             n += (nk + 15) // 16 if nk > 0 else 0
-            if n >= PIPE_CHUNKS:
+            if n >= PIPE_CHUNKS and tag is None:
                 self._pipe.submit(piece, base)
                 base = None if base is None else base + n
                 piece, n = [], 0
-        if piece:
-            self._pipe.submit(piece, base)
+        if piece or tag is not None:
+            self._pipe.submit(piece, base, tag)
 
 
 class _Slot:
@@ -277,7 +278,7 @@ class _ReadPipeline:
             self.stats["allocs"] += sl.fit(n_bases, n_reads, n_chunks)
         return sl
 
-    def submit(self, reads, chunk_id_base=None):
+    def submit(self, reads, chunk_id_base=None, tag=None):
         if self.err:
             raise self.err
         self._ensure_writer()
@@ -313,7 +314,7 @@ class _ReadPipeline:
             off_host.copy_(raw_off, non_blocking=True)
             off_ev = torch.cuda.Event()
             off_ev.record(self.copy)
-        cur = dict(names=names, off_host=off_host, off_ev=off_ev, slot=slot, n_chunks=n_chunks)
+        cur = dict(names=names, off_host=off_host, off_ev=off_ev, slot=slot, n_chunks=n_chunks, tag=tag)
         if PIPE_TRACE:
             cur["trace"] = dict(t_sub=t_sub, t_packed=t_packed, t_enq=time.perf_counter(), ev_start=ev_start, ev_done=done)
         self.stats["h2d_bytes"] += n_bases + 16 * (n_reads + 1)
@@ -352,7 +353,10 @@ class _ReadPipeline:
                 sig = b["slot"].sig.numpy()
                 w = self.m.out_writer
                 if w is not None and hasattr(w, "save_flat"):
-                    w.save_flat(b["names"], sig, off)      # one contiguous buffer + offsets: no per-read Python work
+                    if b.get("tag") is not None:           # sharded run: ordered write into the shared output file
+                        w.save_flat(b["names"], sig, off, tag=b["tag"])
+                    else:
+                        w.save_flat(b["names"], sig, off)  # one contiguous buffer + offsets: no per-read Python work
                 elif w is not None and not getattr(w, "appendable", True):
                     # a writer that cannot append (POD5: inference.py:71-79 sets export_every_n_samples = inf, all reads
                     # are kept and written once at on_predict_epoch_end): keep copies, the staging slot is recycled

@@ -229,8 +229,9 @@ def sampling_iter(num_seqs, genome_seqs, genome_lens, r, seed, total_len, distr,
     """``sampling`` as a generator: the same reads in the same order (the same calls on the ``random`` module and the
     same per-read seeds), produced on demand so that the caller can overlap sampling with the GPU.
 
-    ``window=(lo, hi)`` yields only the accepted reads number ``lo <= i < hi`` (a rank's shard) and stops after
-    ``hi``; ``lengths_only`` yields the length of every accepted read instead of the read.  Reads that are not
+    ``window=(lo, hi)`` — or a sorted list of such disjoint ranges (a rank's batches of a round-robin sharded run) —
+    yields only the accepted reads number ``lo <= i < hi`` and stops after the last ``hi``; ``lengths_only`` yields the
+    length of every accepted read instead of the read.  Reads that are not
     materialised still consume exactly the ``random`` calls the reference would make for them (start position,
     strand, one ``choice`` per ``N``), so every rank of a sharded run sees the same read list without building it:
     the acceptance test of ``read_check`` is evaluated on (start, length) and ``str.count`` over the genome span
@@ -238,7 +239,15 @@ def sampling_iter(num_seqs, genome_seqs, genome_lens, r, seed, total_len, distr,
     draw = DISTR_FUNCS[distr]
     total_genome_len = sum(genome_lens)
     dna = profile.startswith("dna")
-    lo, hi = window if window is not None else (0, None)
+    if window is None:
+        windows = [(0, None)]
+    elif len(window) == 2 and not isinstance(window[0], (tuple, list)):
+        windows = [tuple(window)]
+    else:
+        windows = [tuple(w) for w in window if w[1] > w[0]] or [(0, 0)]
+    wi = 0
+    lo, hi = windows[0]
+    last_hi = windows[-1][1]
     # first-attempt lengths of all reads in one vectorised pass (default law, 32-bit seeds); retries and the other
     # laws take the per-seed path.  Identical values either way.
     # (computed block by block on demand: a block's arrays stay in cache and the first read is not held up by the rest)
@@ -250,8 +259,11 @@ def sampling_iter(num_seqs, genome_seqs, genome_lens, r, seed, total_len, distr,
     accepted = 0
     randint, choice = random.randint, random.choice
     for read_i in range(num_seqs):
-        if hi is not None and accepted >= hi:
+        if last_hi is not None and accepted >= last_hi:
             return
+        while hi is not None and accepted >= hi and wi + 1 < len(windows):   # next window of this rank
+            wi += 1
+            lo, hi = windows[wi]
         retries = 0
         while retries < max_retries:
             start_pos = randint(0, total_genome_len - 1)
@@ -287,7 +299,7 @@ def sampling_iter(num_seqs, genome_seqs, genome_lens, r, seed, total_len, distr,
                 if debug:
                     logger.debug(f"Too many 'N' bases ({count_n} out of {read_length}) for read {read_i}")
             if ok:
-                wanted = accepted >= lo and not lengths_only
+                wanted = accepted >= lo and (hi is None or accepted < hi) and not lengths_only
                 if wanted:
                     read = genome[start_index:start_index + got]
                     if count_n:
@@ -320,11 +332,15 @@ def export_fasta(read_l: Iterable[str], fasta) -> str:
     return out_file
 
 
-def yield_reads(reads: Iterable[str], cheap_names: bool = False, first: int = 0):
+def yield_reads(reads: Iterable[str], cheap_names: bool = False, first=0):
     """utils.py:489-490: ``(read, uuid4 name)``.  ``cheap_names``: the names are only dictionary keys (the writers
     replace them with indexed ids unless ``--preserve-read-ids``), so a counter (starting at ``first``, the global
-    index of a shard's first read) does instead of 100k ``uuid4()`` calls."""
+    index of a shard's first read; or the global indices themselves as a list of ``(lo, hi)`` ranges) does instead of
+    100k ``uuid4()`` calls."""
     if cheap_names:
+        if isinstance(first, (list, tuple)):
+            idx = itertools.chain.from_iterable(range(lo, hi) for lo, hi in first)
+            return ((read, f"read_{i}") for i, read in zip(idx, reads))
         return ((read, f"read_{i}") for i, read in enumerate(reads, first))
     return ((read, str(uuid4())) for read in reads)
 
@@ -359,6 +375,8 @@ def sample_reads_from_reference(genome_seqs, genome_lens, n, r, c, config, fasta
                            window=window, lengths_only=lengths_only)
         if lengths_only:
             return it, None
+        if window and isinstance(window[0], (tuple, list)):
+            return yield_reads(it, cheap_names, first=list(window)), None
         return yield_reads(it, cheap_names, first=window[0] if window else 0), None
     read_list = sampling(seq_num, genome_seqs, genome_lens, r, seed, total_len, distr, profile, min_read_len)
     total_l = sum(round(len(read) / config["max_dna_len"]) for read in read_list)
@@ -389,6 +407,39 @@ def get_reads(fasta, read_input, n, r, c, config, distr, seed, profile, min_read
     reads_fasta, total_l = sample_reads_from_reference(genome_seqs, genome_lens, n, r, c, config, fasta, seed, save,
                                                        distr, profile, min_read_len, stream, cheap_names)
     return read_fasta(reads_fasta, is_rna) if save else (reads_fasta, total_l)
+
+
+def get_reads_batches(fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len, rank, world, plan_fn,
+                      chunks_fn, cheap_names=False):
+    """The reads of rank ``rank`` of a ``world``-process run whose BATCHES are dealt round-robin: ``(iterator of
+    (sequence, name) over the rank's batches in order, plan, chunk counts of all reads)`` with ``plan = plan_fn(counts)``
+    the list of ``(lo, hi)`` read ranges of all batches; batch ``b`` belongs to rank ``b % world``.  Every rank derives
+    the same read list and the same plan from the seed (lengths-only replay of the sampler, about 3 us per read) and
+    materialises only its own batches, lazily, while its GPU works."""
+    k = config["seq_kmer"]
+    if read_input:
+        reads, _ = get_reads(fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len)
+        reads = list(reads)     # read mode samples references to the input reads: nothing to save
+        counts = np.asarray([chunks_fn(len(s), k) for s, _ in reads], dtype=np.int64)
+        plan = plan_fn(counts)
+        mine = [plan[b] for b in range(rank, len(plan), world)]
+        return itertools.chain.from_iterable(reads[lo:hi] for lo, hi in mine), plan, counts
+    logger.info("Reference mode.")
+    genome_seqs, genome_lens = preprocess_genome(fasta)
+    state = random.getstate()
+    lens, _ = sample_reads_from_reference(genome_seqs, genome_lens, n, r, c, config, fasta, seed, False, distr, profile,
+                                          min_read_len, stream=True, lengths_only=True)
+    lens = np.fromiter(lens, dtype=np.int64)
+    random.setstate(state)
+    nk = lens - k + 1
+    counts = np.where(nk > 0, -(-nk // config["max_dna_len"]), 0)
+    plan = plan_fn(counts)
+    mine = [plan[b] for b in range(rank, len(plan), world)]
+    if not mine:
+        return iter(()), plan, counts
+    reads, _ = sample_reads_from_reference(genome_seqs, genome_lens, n, r, c, config, fasta, seed, False, distr,
+                                           profile, min_read_len, stream=True, cheap_names=cheap_names, window=mine)
+    return reads, plan, counts
 
 
 def get_reads_shard(fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len, rank, world, shard_fn,

@@ -131,6 +131,60 @@ class _WriterBase:
                 np.random.normal(self.offset, self.offset_std))
 
 
+class SharedOrder:
+    """Hand-over table of a multi-process run that writes ONE output file: for every batch ``b`` (batches are dealt to
+    the ranks round-robin, in read order) the totals of all batches before it — emitted samples (the records'
+    ``start_time``), written records (position in the per-record NumPy draw stream) and the byte offset in the file.
+    The owner of batch ``b`` publishes the first two for ``b + 1`` as soon as its signal is on the host and the third as
+    soon as its records are encoded, so the ranks encode and ``pwrite`` in parallel and nothing is spliced afterwards.
+    The table is an ``int64`` memory map shared by the ranks of one node (x86 stores are ordered: a row's flag is written
+    after its values)."""
+    COLS = 6   # samples, records, ready1 | offset, ready2, (spare)
+
+    def __init__(self, path: str, n_batches: int, create: bool):
+        import numpy as np
+        self.path, self.n_batches = path, int(n_batches)
+        shape = (self.n_batches + 1, self.COLS)
+        if create:
+            with open(path, "wb") as f:
+                f.truncate(8 * shape[0] * shape[1])
+        self.tab = np.memmap(path, dtype=np.int64, mode="r+", shape=shape)
+
+    def _wait(self, b: int, col: int, timeout: float = 3600.0):
+        import time
+        t0 = time.monotonic()
+        while not self.tab[b, col]:
+            if time.monotonic() - t0 > timeout:
+                raise TimeoutError(f"ordered write: batch {b} was never released (did another rank fail?)")
+            time.sleep(2e-5)
+
+    def start(self, header_bytes: int):
+        self.tab[0, 0], self.tab[0, 1], self.tab[0, 3] = 0, 0, int(header_bytes)
+        self.tab[0, 2] = self.tab[0, 4] = 1
+
+    def totals_before(self, b: int):
+        self._wait(b, 2)
+        return int(self.tab[b, 0]), int(self.tab[b, 1])
+
+    def publish_totals(self, b: int, samples: int, records: int):
+        self.tab[b, 0], self.tab[b, 1] = int(samples), int(records)
+        self.tab[b, 2] = 1
+
+    def offset_of(self, b: int) -> int:
+        self._wait(b, 4)
+        return int(self.tab[b, 3])
+
+    def publish_offset(self, b: int, offset: int):
+        self.tab[b, 3] = int(offset)
+        self.tab[b, 4] = 1
+
+    def close(self):
+        if self.tab is not None:
+            self.tab.flush()
+            del self.tab
+            self.tab = None
+
+
 class BLOW5Writer(_WriterBase):
     """Export signal predictions to a slow5/blow5 file (signal_io.py:62-172)."""
 
@@ -142,6 +196,9 @@ class BLOW5Writer(_WriterBase):
         if comp not in ("none", "zlib"):
             raise ValueError("record compression must be 'none' or 'zlib'")
         self.record_compression = 1 if comp == "zlib" else 0
+        self.shared: Optional[SharedOrder] = None   # multi-process run: ordered writes into one shared file
+        self._fd = -1
+        self._draws_used = 0                          # records whose (median_before, offset) draws this process has made
 
     def _header_attrs(self) -> str:
         seq_kit, flow_cell = get_seq_kit_and_flow_cell(self.profile_name)
@@ -196,12 +253,108 @@ class BLOW5Writer(_WriterBase):
             _lib.check_blow5(lib.s2s_blow5_close(handle), "s2s_blow5_close")
 
 
-    def save_flat(self, names, flat: np.ndarray, offsets: np.ndarray):
+    # ---- multi-process ordered writing ----------------------------------------------------------------------
+    def begin_shared(self, shared: SharedOrder, rank: int):
+        """Open the (one) output file for ordered writing; rank 0 writes the header and releases batch 0."""
+        lib = _lib.load_blow5()
+        self.shared = shared
+        filename = str(self.filename)
+        self._fmt = 1 if filename.endswith(".slow5") else 0
+        if rank == 0:
+            buf, size = C.c_void_p(), C.c_int64()
+            _lib.check_blow5(lib.s2s_blow5_header(self._fmt, self.record_compression, self._header_attrs().encode(),
+                                                  C.byref(buf), C.byref(size)), "s2s_blow5_header")
+            try:
+                with open(filename, "wb") as f:
+                    f.write(C.string_at(buf, size.value))
+                    if shared.n_batches == 0 and self._fmt == 0:
+                        f.write(b"5WOLB")
+            finally:
+                lib.s2s_blow5_free(buf)
+            shared.start(size.value)
+        else:
+            shared.offset_of(0)                 # the file exists once batch 0 has been released
+        self._fd = os.open(filename, os.O_RDWR)
+
+    def end_shared(self):
+        if self._fd >= 0:
+            os.close(self._fd)
+            self._fd = -1
+        if self.shared is not None:
+            self.shared.close()
+
+    def _save_flat_shared(self, names, flat, offsets, tag):
+        """Batch ``b`` (reads ``read_base ..``) of a shared-file run: numbering by global read index, ``start_time`` and
+        the position in the NumPy draw stream from the totals of the batches before it, bytes at the offset handed over
+        by the previous batch's owner.  The file equals the one a single process writes for the same seed."""
+        b, read_base = tag
+        sh = self.shared
+        n_all = len(names)
+        lens = np.diff(np.asarray(offsets[: n_all + 1], dtype=np.int64))
+        keep = np.flatnonzero(lens > 0)
+        n = int(keep.size)
+        klens = lens[keep]
+        out_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(klens, out=out_off[1:])
+        samples0, records0 = sh.totals_before(b)
+        sh.publish_totals(b + 1, samples0 + int(out_off[-1]), records0 + n)     # the next owner can go on at once
+        lib = _lib.load_blow5()
+        buf, size = C.c_void_p(), C.c_int64(0)
+        if n:
+            if n == n_all:
+                sig = np.ascontiguousarray(flat[int(offsets[0]):int(offsets[n_all])], dtype=np.int16)
+            else:
+                sig = np.ascontiguousarray(np.concatenate([flat[int(offsets[i]):int(offsets[i + 1])] for i in keep]),
+                                           dtype=np.int16)
+            if self.ideal_mode:
+                med_v = np.full(n, self.median_before, np.float64)
+                off_v = np.full(n, self.offset, np.float64)
+            else:   # the single-process stream: one (median_before, offset) pair per written record, in record order
+                skip = records0 - self._draws_used
+                if skip > 0:
+                    np.random.standard_normal(2 * skip)
+                draws = np.random.normal([self.median_before, self.offset], [self.median_before_std, self.offset_std],
+                                         size=(n, 2))
+                self._draws_used = records0 + n
+                med_v, off_v = np.ascontiguousarray(draws[:, 0]), np.ascontiguousarray(draws[:, 1])
+            idx = (read_base + keep).astype(np.int64)
+            if self.preserve_read_ids:
+                ids = b"".join(str(names[i]).encode() + b"\0" for i in keep)
+            else:
+                ids = b"".join(b"00000000-0000-0000-0000-%012d\0" % (int(i) + 1) for i in idx)
+            rnum = idx.astype(np.int32)
+            stime = (samples0 + out_off[:-1]).astype(np.uint64)
+            p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+            _lib.check_blow5(lib.s2s_blow5_encode_batch(self._fmt, self.record_compression, n, ids, p(sig), p(out_off),
+                                                        p(off_v), p(med_v), p(rnum), p(stime), self.digitisation,
+                                                        self.signal_range, self.sample_rate, self.n_threads,
+                                                        C.byref(buf), C.byref(size)), "s2s_blow5_encode_batch")
+        try:
+            at = sh.offset_of(b)
+            sh.publish_offset(b + 1, at + size.value)
+            if size.value and not os.environ.get("S2S_BLOW5_NULL_SINK"):    # (developer switch: encode, do not write)
+                view = memoryview((C.c_char * size.value).from_address(buf.value))
+                done = 0
+                while done < size.value:
+                    done += os.pwrite(self._fd, view[done:], at + done)
+            if b == sh.n_batches - 1 and self._fmt == 0:
+                os.pwrite(self._fd, b"5WOLB", at + size.value)
+        finally:
+            if buf.value:
+                lib.s2s_blow5_free(buf)
+        self.reads_written += n
+        self.samples_written += int(out_off[-1])
+
+    def save_flat(self, names, flat: np.ndarray, offsets: np.ndarray, tag=None):
         """Fast path of the read pipeline: the digitised signals of a batch as ONE contiguous int16 array plus per-read
         offsets (read i = flat[offsets[i]:offsets[i+1]], in `names` order).  Writes exactly the records that
         ``signals = {name: flat[...]}; save()`` writes — same numbering, same order of the per-record NumPy draws, empty
         reads skipped — with the per-read Python work (two scalar draws, a UUID object, a bytes append, a second copy
         of every signal) replaced by array operations: the writer thread shares the GIL with the read sampler."""
+        if self.shared is not None:
+            if tag is None:
+                raise RuntimeError("shared-file writing needs the batch tag (batch index, first global read)")
+            return self._save_flat_shared(names, flat, offsets, tag)
         n_all = len(names)
         lens = np.diff(np.asarray(offsets[: n_all + 1], dtype=np.int64))
         base = self._id_base

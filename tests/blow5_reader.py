@@ -51,6 +51,14 @@ def read_blow5(path):
                 attrs=attrs, types=types, names=names, records=records)
 
 
+def record_span(path):
+    """(first byte of the first record, first byte of the end marker) of a BLOW5 file."""
+    data = open(path, "rb").read()
+    assert data[:6] == b"BLOW5\x01" and data[-5:] == b"5WOLB"
+    (hsize,) = struct.unpack_from("<I", data, 64)
+    return 68 + hsize, len(data) - 5
+
+
 def read_slow5(path):
     lines = open(path).read().split("\n")
     assert lines[0] == "#slow5_version\t0.2.0" and lines[1] == "#num_read_groups\t1"

@@ -199,8 +199,9 @@ def test_cli_predict_reference_mode_deterministic(golden_dir, tmp_path, profile,
 
 def test_cli_two_ranks_equal_one_rank(golden_dir, tmp_path):
     """`torchrun --nproc-per-node 2 -m seq2squiggle_b200 predict ...` (both ranks on this GPU) writes the same records as
-    the single-process command: reads are sharded by chunk count, Philox is keyed by the global chunk index, rank 0
-    stitches the part files (read ids / read_number / start_time continue across parts)."""
+    the single-process command: the batches of the read list are dealt to the ranks round-robin, Philox is keyed by the
+    global chunk index, and both ranks write their records into the one output file in read order (read ids,
+    read_number, start_time AND the per-record offset / median_before draws equal the single-process file's)."""
     path, sd, cfg = _ckpt(golden_dir)
     rng = np.random.default_rng(17)
     fasta = tmp_path / "genome.fasta"
@@ -208,19 +209,22 @@ def test_cli_two_ranks_equal_one_rank(golden_dir, tmp_path):
     fasta.write_text(">chr1\n" + "\n".join(g[i:i + 70] for i in range(0, len(g), 70)) + "\n")
     args = [str(fasta), "-m", path, "-n", "300", "-r", "500", "-s", "5", "--profile", "dna-r10-prom", "--noise-std", "2.0"]
     one, two = tmp_path / "one.blow5", tmp_path / "two.blow5"
+    env = dict(os.environ, S2S_PIPE_CHUNKS="1500")      # about seven batches: both ranks get several
     res = subprocess.run([sys.executable, "-m", "seq2squiggle_b200", "predict", *args, "-o", str(one)], cwd=ROOT,
-                         capture_output=True, text=True, timeout=600)
+                         capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0, res.stderr[-2000:]
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", "29577", "-m", "seq2squiggle_b200", "predict",
-                          *args, "-o", str(two)], cwd=ROOT, capture_output=True, text=True, timeout=600)
+                          *args, "-o", str(two)], cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0, res.stderr[-3000:]
+    assert "of 7 batches" in res.stderr or "batches" in res.stderr
     a, b = read_blow5(str(one)), read_blow5(str(two))
     assert len(a["records"]) == len(b["records"]) > 250
-    assert not list(tmp_path.glob("*.part*"))
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["genome.fasta", "one.blow5", "two.blow5"]   # no parts, no table
+    assert len({r["offset"] for r in a["records"]}) > 100           # samplers on: per-record draws
     for i, (x, y) in enumerate(zip(a["records"], b["records"])):
-        assert x["signal"] == y["signal"] and x["read_id"] == y["read_id"]
-        assert y["read_number"] == i and x["start_time"] == y["start_time"]
+        assert x == y, i
+        assert y["read_number"] == i
 
 
 def test_inference_run_read_mode_samplers_on(golden_dir, tmp_path):

@@ -165,82 +165,76 @@ def test_pack_reads_variants_agree():
     assert joined == b"" and ro2.tolist() == [0] and co2.tolist() == [0]
 
 
-def test_merge_blow5_parts_equals_single_writer(tmp_path):
-    from seq2squiggle_b200.inference import merge_blow5_parts
-    from seq2squiggle_b200.profiles import get_profile
-    from seq2squiggle_b200.signal_io import BLOW5Writer
-    from tests.blow5_reader import read_blow5
-    rng = np.random.default_rng(3)
-    prof = get_profile("dna-r10-prom")
-    sigs = {f"r{i}": rng.integers(-100, 900, size=int(rng.integers(1, 300))).astype(np.int16) for i in range(11)}
-    names = list(sigs)
-    single = BLOW5Writer(str(tmp_path / "single.blow5"), prof, True, "dna-r10-prom", False)
-    single.signals = sigs
-    single.save()
-    parts = []
-    for r, (lo, hi) in enumerate(((0, 4), (4, 4), (4, 11))):             # middle rank owns no reads
-        w = BLOW5Writer(str(tmp_path / f"o.blow5.part{r}"), prof, True, "dna-r10-prom", False)
-        w.signals = {n: sigs[n] for n in names[lo:hi]}
-        w.save()
-        parts.append(w.filename)
-    nr, ns = merge_blow5_parts(str(tmp_path / "o.blow5"), parts, preserve_read_ids=False)
-    a, b = read_blow5(str(tmp_path / "single.blow5")), read_blow5(str(tmp_path / "o.blow5"))
-    assert nr == 11 and ns == sum(len(v) for v in sigs.values())
-    assert a["records"] == b["records"]
+def test_plan_batches():
+    """Batches of a sharded run: contiguous, complete, a read is never split, every batch but the last reaches the
+    target, and the rule equals predict_reads' own piece rule (one batch = one pipeline piece)."""
+    from seq2squiggle_b200.inference import chunks_of_read, plan_batches
+    rng = np.random.default_rng(1)
+    counts = [chunks_of_read(int(l), 9) for l in rng.integers(1, 4000, size=700)]
+    plan = plan_batches(counts, 2000)
+    assert plan[0][0] == 0 and plan[-1][1] == len(counts) and all(a[1] == b[0] for a, b in zip(plan, plan[1:]))
+    sizes = [sum(counts[lo:hi]) for lo, hi in plan]
+    assert all(s >= 2000 for s in sizes[:-1]) and max(sizes) < 2000 + 250
+    # the piece rule of model.predict_reads: close the piece with the read that reaches the target
+    ref, cur, n, lo = [], 0, 0, 0
+    for i, c in enumerate(counts):
+        n += c
+        if n >= 2000:
+            ref.append((lo, i + 1)); lo, n = i + 1, 0
+    if lo < len(counts):
+        ref.append((lo, len(counts)))
+    assert plan == ref
+    assert plan_batches([], 10) == [] and plan_batches([0, 0, 0], 10) == [(0, 3)] and plan_batches([50], 10) == [(0, 1)]
 
 
-@pytest.mark.parametrize("kernel_copy", [True, False])
-def test_splice_blow5_parts_equals_single_writer(tmp_path, monkeypatch, kernel_copy):
-    """The parallel end of a sharded run, driven serially here: a fake process group hands every "rank" the gathered
-    (bytes, samples, header) triples; rank 0's part becomes the output, the others splice themselves in (with and
-    without os.copy_file_range).  A rank without reads, a rank whose reads are all empty, skipped (empty) reads inside
-    a shard: record bytes equal to one writer's."""
-    import os
-    from seq2squiggle_b200 import inference as inf
+@pytest.mark.parametrize("samplers", [False, True])
+def test_ordered_shared_file_equals_single_writer(tmp_path, samplers):
+    """signal_io.SharedOrder + BLOW5Writer.begin_shared: three "ranks" (forked processes here, torchrun ranks in a run) write
+    their round-robin batches into ONE file in whatever order their turn comes — a batch without reads, a batch whose
+    reads are all empty, skipped (empty) reads inside a batch; with the samplers on every rank replays the single
+    per-record NumPy draw stream.  Record bytes (and the end marker) equal one writer's."""
     from seq2squiggle_b200.profiles import get_profile
-    from seq2squiggle_b200.signal_io import BLOW5Writer
-    if not kernel_copy:
-        monkeypatch.delattr(os, "copy_file_range", raising=False)
+    from seq2squiggle_b200.signal_io import BLOW5Writer, SharedOrder
+    from tests.blow5_reader import read_blow5, record_span
     rng = np.random.default_rng(4)
     prof = get_profile("dna-r10-prom")
-    sigs = {f"r{i}": rng.integers(-100, 900, size=0 if i in (2, 7, 8) else int(rng.integers(1, 300))).astype(np.int16)
-            for i in range(13)}
-    names = list(sigs)
-    single = BLOW5Writer(str(tmp_path / "single.blow5"), prof, True, "dna-r10-prom", False)
-    single.signals = sigs
-    single.save()
-    shards = ((0, 4), (4, 4), (4, 7), (7, 9), (9, 13))                    # rank 1: no reads; rank 3: only empty reads
+    sigs = [rng.integers(-100, 900, size=0 if i in (2, 7, 8) else int(rng.integers(1, 300))).astype(np.int16)
+            for i in range(23)]
+    names = [f"r{i}" for i in range(23)]
+    flat = np.concatenate(sigs)
+    off = np.concatenate([[0], np.cumsum([len(x) for x in sigs])]).astype(np.int64)
+    np.random.seed(11)
+    single = BLOW5Writer(str(tmp_path / "single.blow5"), prof, not samplers, "dna-r10-prom", False)
+    single.save_flat(names, flat, off)
+    plan = [(0, 4), (4, 7), (7, 9), (9, 13), (13, 13), (13, 20), (20, 23)]     # batch 2: only empty reads; batch 4: no reads
     out = str(tmp_path / "o.blow5")
-    writers = []
-    for r, (lo, hi) in enumerate(shards):
-        w = BLOW5Writer(inf.part_path(out, r), prof, True, "dna-r10-prom", False)
-        w._id_base = lo
-        w.signals = {n: sigs[n] for n in names[lo:hi]}
-        w.save()
-        writers.append(w)
-    info = [(inf.blow5_record_span(w.filename)[1] - inf.blow5_record_span(w.filename)[0], w.samples_written,
-             inf.blow5_record_span(w.filename)[0]) for w in writers]
+    world = 3
+    SharedOrder(out + ".order", len(plan), create=True).close()
 
-    class FakeDist:     # the collective calls of one rank; ranks are run in the order the barriers would enforce
-        @staticmethod
-        def all_gather_object(lst, obj):
-            lst[:] = info
+    def rank_main(r):              # one process per "rank" (its own NumPy stream, like a torchrun rank)
+        np.random.seed(11)
+        w = BLOW5Writer(out, prof, not samplers, "dna-r10-prom", False)
+        w.begin_shared(SharedOrder(out + ".order", len(plan), create=False), r)
+        for b in range(r, len(plan), world):
+            lo, hi = plan[b]
+            w.save_flat(names[lo:hi], flat, off[lo:hi + 1], tag=(b, lo))
+        w.end_shared()
 
-        @staticmethod
-        def barrier():
-            pass
-
-    for r, w in enumerate(writers):                                        # rank 0 first (rename + truncate), then the rest
-        inf.splice_parts_collective(out, w.filename, r, len(shards), w.samples_written, FakeDist)
-    with open(out, "r+b") as f:                                            # rank 0's closing step ran before the others' splices here
-        f.seek(-5, 2)
-        f.write(b"5WOLB")
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    procs = [ctx.Process(target=rank_main, args=(r,)) for r in (2, 1, 0)]           # rank 0 (the header) starts last
+    for p_ in procs:
+        p_.start()
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    a, b = read_blow5(str(tmp_path / "single.blow5")), read_blow5(out)
+    assert a["records"] == b["records"] and len(a["records"]) == 20
     blobs = []
     for path in (str(tmp_path / "single.blow5"), out):
-        lo, hi = inf.blow5_record_span(path)
+        lo, hi = record_span(path)
         blobs.append(open(path, "rb").read()[lo:])
     assert blobs[0] == blobs[1]
-    assert not any(os.path.exists(inf.part_path(out, r)) for r in range(len(shards)))
 
 
 def test_default_config_equals_reference_yaml():
@@ -289,9 +283,9 @@ def test_shipped_library_is_blackwell_native():
         assert found, f"no kernel named *{tag}* in the library"
         return found
 
-    for tag in ("k_tc_attn2", "k_tc_fc_ffn", "k_tc_qkv_plain"):
+    for tag in ("k_tc_attn3", "k_tc_fc_ffn", "k_tc_qkv_plain"):
         for c in kernels(tag):
             assert c["UTCHMMA"] > 0 and c["LDTM"] > 0 and c["UTMALDG"] > 0 and c["SYNCS"] > 0, (tag, dict(c))
-    assert all(c["STTM"] > 0 for c in kernels("k_tc_attn2") + kernels("k_tc_fc_ffn"))   # fp16 P / hidden written back to TMEM
+    assert all(c["STTM"] > 0 for c in kernels("k_tc_attn3") + kernels("k_tc_fc_ffn"))   # fp16 P / hidden written back to TMEM
     assert any(c["UTMASTG"] > 0 for c in kernels("k_tc_fc_ffn"))
-    assert all(c["MUFU"] > 0 for c in kernels("k_tc_attn2"))
+    assert all(c["MUFU"] > 0 for c in kernels("k_tc_attn3"))

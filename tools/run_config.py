@@ -70,6 +70,8 @@ def main():
     ap.add_argument("--out", default=None, help="output file (default: a temporary .blow5; /dev/null is not seekable)")
     ap.add_argument("--seed", type=int, default=11)
     ap.add_argument("--profile", action="store_true", help="cProfile the main thread of inference_run")
+    ap.add_argument("--null-sink", action="store_true",
+                    help="writer -> nowhere: records are encoded (and counted) but not written (the BASELINE configs[4] 'null sink' figure)")
     a = ap.parse_args()
     profile = "dna-r9-min" if a.config == 3 else "dna-r10-prom"
     cfg = update_config(profile, set_config(None))
@@ -91,12 +93,13 @@ def main():
                 f.write(g[i:i + 70] + "\n")
     out = a.out or os.path.join(tmp, "sim.blow5")
     inference.get_reads = timed("get_reads (genome preprocessing + read sampling)", reads_mod.get_reads)
-    inference.get_reads_shard = timed("get_reads_shard (genome preprocessing + lengths-only replay)", reads_mod.get_reads_shard)
-    inference.splice_parts_collective = timed("splice_parts_collective (parallel merge of the parts)", inference.splice_parts_collective)
+    inference.get_reads_batches = timed("get_reads_batches (genome preprocessing + lengths-only replay + batch plan)", reads_mod.get_reads_batches)
     from seq2squiggle_b200 import model as M
     M.seq2squiggle.predict_reads = timed("predict_reads (pack + enqueue, blocks on the previous batch)", M.seq2squiggle.predict_reads)
     M.seq2squiggle.on_predict_epoch_end = timed("on_predict_epoch_end (drain + writer join)", M.seq2squiggle.on_predict_epoch_end)
     M.seq2squiggle.load_from_checkpoint = classmethod(timed("load_from_checkpoint (incl. CUDA context)", M.seq2squiggle.load_from_checkpoint.__func__))
+    if a.null_sink:      # keep every byte of host work but the pwrite / fwrite itself
+        os.environ["S2S_BLOW5_NULL_SINK"] = "1"
     set_seeds(a.seed)
     prof = None
     if a.profile:
@@ -111,7 +114,7 @@ def main():
                             offset_mean=None, offset_std=None, median_before_mean=None, median_before_std=None,
                             min_noise=0.0, min_duration=3, min_read_len=30, preserve_read_ids=False, seed=a.seed)
     wall = time.perf_counter() - t0
-    if int(os.environ.get("RANK", "0")) != 0:      # sharded run: rank 0 holds the merged file and reports
+    if int(os.environ.get("RANK", "0")) != 0:      # sharded run: all ranks wrote into the one file; rank 0 reports
         print(f"rank {os.environ['RANK']}: {wall:.2f} s wall; " + "; ".join(f"{k.split(' (')[0]} {v:.2f} s" for k, v in T.items()))
         return
     if prof:
@@ -119,6 +122,9 @@ def main():
         prof.disable()
         pstats.Stats(prof).sort_stats("tottime").print_stats(18)
     size = os.path.getsize(out) if os.path.exists(out) else 0
+    if a.null_sink:
+        print(f"null sink: {wall:.2f} s wall; " + "; ".join(f"{k.split(' (')[0]} {v:.2f} s" for k, v in T.items()))
+        return
     nrec, nsamp = blow5_summary(out)
     print(f"config {a.config} ({profile}, {'read' if read_input else 'reference'} mode): {nrec} reads, {nsamp} samples, "
           f"{size / 1e6:.1f} MB BLOW5 in {wall:.2f} s wall = {nrec / wall:.0f} reads/s, {nsamp / wall / 1e6:.1f} M samples/s "
