@@ -31,10 +31,10 @@ FLOP_PER_CHUNK = 85_083_392
 ATT_FLOP_PER_CHUNK_LAYER = 16_000_000       # QK^T 8.0 M + PV 8.0 M per decoder layer
 ATT_EXP_PER_CHUNK_LAYER = 8 * 250 * 250     # softmax exponentials per decoder layer
 MUFU_PER_CLK_SM = 16                        # ex2 per clock per SM (4 per SM sub-partition)
-# k_tc_attn3, one launch of 32768 chunks, `ncu --set full` (profiles/r02_attn3_ncu.txt): dram__bytes_read.sum 0.963865 GB
-# + dram__bytes_write.sum 0.917112 GB; the algorithmic traffic is 2 x 256 rows x 128 B = 65,536 B per chunk (x16 in, o16 out)
-# (ncu's figure is below it: part of the o16 stream of one launch is still in the 126 MB L2 when the counters stop)
-ATT_DRAM_BYTES_PER_CHUNK_NCU = (0.963865e9 + 0.917112e9) / 32768
+# k_tc_attn3, one launch of 32768 chunks, `ncu --set full` (profiles/r02_attn3_ncu.txt): dram__bytes_read.sum 1.074546 GB
+# + dram__bytes_write.sum 1.040482 GB; the algorithmic traffic is 2 x 256 rows x 128 B = 65,536 B per chunk (x16 in, o16 out)
+# (ncu's figure is just below it: the tail of the o16 stream is still in the 126 MB L2 when the counters stop)
+ATT_DRAM_BYTES_PER_CHUNK_NCU = (1.074546e9 + 1.040482e9) / 32768
 ATT_ALGO_BYTES_PER_CHUNK = 2 * 256 * 128
 ATT_QKV_FLOP_PER_CHUNK_LAYER = 2 * 256 * 64 * 192          # fused QKV projection inside the attention kernel
 FFN_FLOP_PER_CHUNK_LAYER = 2 * 256 * 64 * (64 + 256 + 256)  # fc + W1 + W2 per decoder layer (256 rows per chunk)

@@ -165,15 +165,21 @@ __global__ void __launch_bounds__(256) k_compact(const float* __restrict__ pa, c
     rd_lo = raw_offsets[lo];
     rd_hi = raw_offsets[lo + 1];
   }
-  for (int t0 = 0; t0 < S2S_L_DEC; t0 += 32) {
-    const int t = t0 + lane;
-    float v = t < S2S_L_DEC ? pa[c * S2S_L_DEC + t] : 0.f;
-    const bool keep = v != 0.f;
+  // all eight loads of the chunk's 250 floats first (independent, 1000 contiguous bytes), then the ordered scatter
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int t = 32 * i + lane;
+    v[i] = t < S2S_L_DEC ? __ldg(pa + c * S2S_L_DEC + t) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool keep = v[i] != 0.f;
     const unsigned m = __ballot_sync(0xffffffffu, keep);
     if (keep) {
       int64_t pos = dst + __popc(m & ((1u << lane) - 1u));
       if (rna_reverse) pos = rd_hi - 1 - (pos - rd_lo);
-      raw[pos] = digitise_one(v, dig, range, offset);
+      raw[pos] = digitise_one(v[i], dig, range, offset);
     }
     dst += __popc(m);
   }
