@@ -9,8 +9,9 @@
  * File layout follows the public SLOW5 specification v0.2.0 (hasindu2008/slow5specs): 64-byte binary file header
  * (magic "BLOW5\1", version, record compression, number of read groups, signal compression), uint32 size +
  * ASCII attribute / column header, length-prefixed records, "5WOLB" end marker.  Record compression: none or
- * zlib; signal compression: none.  slow5lib / pyslow5 are not available in the build image, so byte parity with
- * pyslow5's output is unpinned; the format is pinned by an independent reader in tests/test_signal_io.py.
+ * zlib; signal compression: none or svb-zd (zigzag-delta + StreamVByte, slow5lib's default).  slow5lib / pyslow5 are
+ * not available in the build image, so byte parity with pyslow5's output is unpinned; the format is pinned by an
+ * independent reader (incl. an svb-zd decoder) in tests/blow5_reader.py.
  *
  * All pointers are HOST pointers owned by the caller.  Return 0 on success, <0 on error
  * (s2s_blow5_last_error()).  A handle is not thread-safe; write_batch itself fans out over n_threads.
@@ -27,7 +28,11 @@ extern "C" {
 typedef struct s2s_blow5_writer* s2s_blow5_handle;
 
 enum { S2S_BLOW5_BINARY = 0, S2S_SLOW5_ASCII = 1 };            /* by file extension: .blow5 / .slow5 */
-enum { S2S_BLOW5_COMPRESS_NONE = 0, S2S_BLOW5_COMPRESS_ZLIB = 1 };
+enum { S2S_BLOW5_COMPRESS_NONE = 0, S2S_BLOW5_COMPRESS_ZLIB = 1 };   /* record compression (file header byte 9) */
+enum { S2S_BLOW5_SIGNAL_NONE = 0, S2S_BLOW5_SIGNAL_SVB_ZD = 1 };     /* signal compression (file header byte 14) */
+/* Every `record_compression` argument below carries both: record method | (signal method << 8).  pyslow5's own default
+ * (signal_io.py:98-102 opens with the defaults) is zlib records + svb-zd signal = S2S_BLOW5_COMPRESS_ZLIB |
+ * (S2S_BLOW5_SIGNAL_SVB_ZD << 8). */
 
 const char* s2s_blow5_last_error(void);
 

@@ -58,6 +58,38 @@ std::string fmt_double(double v) {
   return buf;
 }
 
+// ---- svb-zd: the signal compression pyslow5 / slow5lib apply by default (slow5lib src/slow5_press.c, "svb-zd") ----------
+// zigzag-delta of the int16 samples widened to int32 (d_i = x_i - x_{i-1}, x_{-1} = 0, z = (d << 1) ^ (d >> 31)), then
+// StreamVByte (Lemire & Kurz) of the uint32 stream: ceil(n / 4) control bytes (2 bits per value: bytes - 1, value i of a
+// group in bits 2 (i % 4)), then the values' low 1..4 bytes, little endian.  The compressed blob is
+//   uint32 n | control bytes | data bytes,
+// and a record stores it as  uint64 blob_bytes | blob  in place of the raw samples (len_raw_signal still counts samples).
+// slow5lib is not available offline: written from its published algorithm; byte parity with slow5lib is unpinned.
+size_t svb_zd_bound(size_t n) { return 4 + (n + 3) / 4 + 4 * n; }
+
+size_t svb_zd_encode(const int16_t* x, size_t n, unsigned char* out) {
+  const uint32_t n32 = (uint32_t)n;
+  memcpy(out, &n32, 4);
+  unsigned char* ctrl = out + 4;
+  unsigned char* data = ctrl + (n + 3) / 4;
+  int32_t prev = 0;
+  unsigned char key = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const int32_t d = (int32_t)x[i] - prev;
+    prev = x[i];
+    const uint32_t z = ((uint32_t)d << 1) ^ (uint32_t)(d >> 31);
+    unsigned code;
+    if (z < (1u << 8)) { code = 0; data[0] = (unsigned char)z; data += 1; }
+    else if (z < (1u << 16)) { code = 1; data[0] = (unsigned char)z; data[1] = (unsigned char)(z >> 8); data += 2; }
+    else if (z < (1u << 24)) { code = 2; data[0] = (unsigned char)z; data[1] = (unsigned char)(z >> 8); data[2] = (unsigned char)(z >> 16); data += 3; }
+    else { code = 3; memcpy(data, &z, 4); data += 4; }
+    key |= (unsigned char)(code << (2 * (i & 3)));
+    if ((i & 3) == 3) { *ctrl++ = key; key = 0; }
+  }
+  if (n & 3) *ctrl++ = key;
+  return (size_t)(data - out);
+}
+
 std::string sorted_attrs(const char* header_attrs) {
   std::vector<std::pair<std::string, std::string>> kv;
   const char* p = header_attrs ? header_attrs : "";
@@ -94,10 +126,10 @@ std::string header_bytes(int format, int compression, const char* header_attrs) 
     hdr.assign(64, '\0');
     memcpy(&hdr[0], kMagic, 6);
     memcpy(&hdr[6], kVersion, 3);
-    hdr[9] = (char)compression;
+    hdr[9] = (char)(compression & 0xFF);          // record compression: 0 none, 1 zlib
     const uint32_t n_groups = 1;
     memcpy(&hdr[10], &n_groups, 4);
-    hdr[14] = 0;  // signal compression: none
+    hdr[14] = (char)((compression >> 8) & 0xFF);  // signal compression: 0 none, 1 svb-zd
     const uint32_t hsize = (uint32_t)ascii.size();
     hdr.append(reinterpret_cast<const char*>(&hsize), 4);
     hdr += ascii;
@@ -140,23 +172,35 @@ int encode_records(int format, int compression, int64_t n_reads, const char* rea
   if ((int64_t)n_threads > n_reads) n_threads = (int32_t)n_reads;
 
   chunks.assign((size_t)n_threads, std::string());
+  const int rec_comp = compression & 0xFF, sig_comp = (compression >> 8) & 0xFF;
+  // upper bound of a record body (exact when the signal is stored raw)
   auto body_size = [&](int64_t r) -> size_t {
     const size_t n = (size_t)(sig_offsets[r + 1] - sig_offsets[r]);
-    return 2 + id_len[r] + 4 + 32 + 8 + 2 * n + (8 + 1) + 8 + 4 + 1 + 8;
+    const size_t sig_bytes = sig_comp == S2S_BLOW5_SIGNAL_SVB_ZD ? 8 + svb_zd_bound(n) : 2 * n;
+    return 2 + id_len[r] + 4 + 32 + 8 + sig_bytes + (8 + 1) + 8 + 4 + 1 + 8;
   };
-  auto fill_body = [&](int64_t r, char* q) {
+  // writes the body at q, returns its size
+  auto fill_body = [&](int64_t r, char* q) -> size_t {
+    char* const q0 = q;
     const uint64_t n = (uint64_t)(sig_offsets[r + 1] - sig_offsets[r]);
     put<uint16_t>(q, (uint16_t)id_len[r]);
     memcpy(q, ids[r], id_len[r]); q += id_len[r];
     put<uint32_t>(q, 0u);
     put<double>(q, digitisation); put<double>(q, offset[r]); put<double>(q, range); put<double>(q, sampling_rate);
     put<uint64_t>(q, n);
-    memcpy(q, signal + sig_offsets[r], 2 * n); q += 2 * n;
+    if (sig_comp == S2S_BLOW5_SIGNAL_SVB_ZD) {
+      const uint64_t cb = (uint64_t)svb_zd_encode(signal + sig_offsets[r], (size_t)n, reinterpret_cast<unsigned char*>(q + 8));
+      put<uint64_t>(q, cb);
+      q += cb;
+    } else {
+      memcpy(q, signal + sig_offsets[r], 2 * n); q += 2 * n;
+    }
     put<uint64_t>(q, 1ull); *q++ = '0';           // channel_number "0"
     put<double>(q, median_before[r]);
     put<int32_t>(q, read_number[r]);
     put<uint8_t>(q, 0);                           // start_mux
     put<uint64_t>(q, start_time[r]);
+    return (size_t)(q - q0);
   };
   std::vector<int> status((size_t)n_threads, 0);
   auto work = [&](int t) {
@@ -179,25 +223,24 @@ int encode_records(int format, int compression, int64_t n_reads, const char* rea
       }
       return;
     }
-    if (compression == S2S_BLOW5_COMPRESS_NONE) {
+    if (rec_comp == S2S_BLOW5_COMPRESS_NONE) {
       size_t total = 0;
       for (int64_t r = lo; r < hi; ++r) total += 8 + body_size(r);
       out.resize(total);
       char* q = &out[0];
       for (int64_t r = lo; r < hi; ++r) {
-        const size_t bs = body_size(r);
+        const size_t bs = fill_body(r, q + 8);
         put<uint64_t>(q, (uint64_t)bs);
-        fill_body(r, q);
         q += bs;
       }
+      out.resize((size_t)(q - &out[0]));
       return;
     }
     std::vector<char> body;
     std::vector<unsigned char> comp;
     for (int64_t r = lo; r < hi; ++r) {
-      const size_t bs = body_size(r);
-      body.resize(bs);
-      fill_body(r, body.data());
+      body.resize(body_size(r));
+      const size_t bs = fill_body(r, body.data());
       uLongf clen = compressBound((uLong)bs);
       comp.resize(clen);
       if (compress2(comp.data(), &clen, reinterpret_cast<const Bytef*>(body.data()), (uLong)bs, Z_DEFAULT_COMPRESSION) != Z_OK) {
@@ -232,8 +275,9 @@ int s2s_blow5_open(const char* path, int format, int append, int record_compress
   if (!out || !path) { set_error("null argument"); return -1; }
   *out = nullptr;
   if (format != S2S_BLOW5_BINARY && format != S2S_SLOW5_ASCII) { set_error("unknown format %d", format); return -1; }
-  if (record_compression != S2S_BLOW5_COMPRESS_NONE && record_compression != S2S_BLOW5_COMPRESS_ZLIB) {
-    set_error("unknown record compression %d", record_compression);
+  if ((record_compression & 0xFF) > S2S_BLOW5_COMPRESS_ZLIB || ((record_compression >> 8) & 0xFF) > S2S_BLOW5_SIGNAL_SVB_ZD ||
+      record_compression < 0 || record_compression > 0xFFFF) {
+    set_error("unknown record / signal compression 0x%x", record_compression);
     return -1;
   }
   s2s_blow5_writer* w = new s2s_blow5_writer();
@@ -248,9 +292,9 @@ int s2s_blow5_open(const char* path, int format, int append, int record_compress
       if (fread(head, 1, 16, w->fp) != 16 || memcmp(head, kMagic, 6) != 0) {
         set_error("%s is not a BLOW5 file", path); fclose(w->fp); delete w; return -1;
       }
-      w->compression = head[9];
-      if (w->compression != S2S_BLOW5_COMPRESS_NONE && w->compression != S2S_BLOW5_COMPRESS_ZLIB) {
-        set_error("%s uses record compression %d, which this writer cannot append to", path, w->compression);
+      w->compression = head[9] | (head[14] << 8);
+      if (head[9] > S2S_BLOW5_COMPRESS_ZLIB || head[14] > S2S_BLOW5_SIGNAL_SVB_ZD) {
+        set_error("%s uses record / signal compression %d / %d, which this writer cannot append to", path, head[9], head[14]);
         fclose(w->fp); delete w; return -1;
       }
       char tail[5];

@@ -192,10 +192,14 @@ class BLOW5Writer(_WriterBase):
                  record_compression: Optional[str] = None):
         super().__init__(filename, profile, ideal_mode, profile_name, preserve_read_ids)
         self.n_threads = n_threads or min(os.cpu_count() or 1, 32)
-        comp = (record_compression or os.environ.get("S2S_BLOW5_COMPRESS", "none")).lower()
-        if comp not in ("none", "zlib"):
-            raise ValueError("record compression must be 'none' or 'zlib'")
-        self.record_compression = 1 if comp == "zlib" else 0
+        # record | signal compression.  pyslow5's defaults (what the reference's writer gets, signal_io.py:98-102) are
+        # zlib records + svb-zd signal = "zlib+svb-zd"; "none" (the default here) writes raw records at memory speed
+        comp = (record_compression or os.environ.get("S2S_BLOW5_COMPRESS", "none")).lower().replace("_", "-")
+        table = {"none": 0, "zlib": 1, "svb-zd": 1 << 8, "zlib+svb-zd": 1 | (1 << 8), "svb-zd+zlib": 1 | (1 << 8),
+                 "pyslow5": 1 | (1 << 8)}
+        if comp not in table:
+            raise ValueError("BLOW5 compression must be one of 'none', 'zlib', 'svb-zd', 'zlib+svb-zd'")
+        self.record_compression = table[comp]
         self.shared: Optional[SharedOrder] = None   # multi-process run: ordered writes into one shared file
         self._fd = -1
         self._draws_used = 0                          # records whose (median_before, offset) draws this process has made

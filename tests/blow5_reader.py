@@ -4,6 +4,26 @@ import struct
 import zlib
 
 
+def svb_zd_decode(blob):
+    """slow5lib's "svb-zd" signal compression, decoded independently of csrc/blow5_writer.cpp: uint32 count, StreamVByte
+    control bytes (2 bits per value = bytes - 1, value i of a group of four in bits 2 (i % 4)), little-endian data
+    bytes; zigzag + delta (first delta against 0) back to int16."""
+    (n,) = struct.unpack_from("<I", blob, 0)
+    n_ctrl = (n + 3) // 4
+    ctrl, pos = blob[4:4 + n_ctrl], 4 + n_ctrl
+    out, prev = [], 0
+    for i in range(n):
+        nb = ((ctrl[i >> 2] >> (2 * (i & 3))) & 3) + 1
+        z = int.from_bytes(blob[pos:pos + nb], "little")
+        pos += nb
+        d = (z >> 1) ^ -(z & 1)
+        prev += d
+        assert -32768 <= prev <= 32767
+        out.append(prev)
+    assert pos == len(blob), "svb-zd blob size"
+    return out
+
+
 def read_blow5(path):
     data = open(path, "rb").read()
     assert data[:6] == b"BLOW5\x01", "magic"
@@ -35,7 +55,13 @@ def read_blow5(path):
         (group,) = struct.unpack_from("<I", body, q); q += 4
         dig, off, rng, rate = struct.unpack_from("<dddd", body, q); q += 32
         (n,) = struct.unpack_from("<Q", body, q); q += 8
-        sig = struct.unpack_from(f"<{n}h", body, q); q += 2 * n
+        if sig_comp == 1:
+            (cb,) = struct.unpack_from("<Q", body, q); q += 8
+            sig = svb_zd_decode(body[q:q + cb]); q += cb
+            assert len(sig) == n
+        else:
+            assert sig_comp == 0
+            sig = struct.unpack_from(f"<{n}h", body, q); q += 2 * n
         (cl,) = struct.unpack_from("<Q", body, q); q += 8
         chan = body[q:q + cl].decode(); q += cl
         (med,) = struct.unpack_from("<d", body, q); q += 8

@@ -83,8 +83,9 @@ RUN_WORKER = textwrap.dedent("""
 """)
 
 
-def _run(tmp_path, script, fasta, out, mode, samplers, seed, world):
+def _run(tmp_path, script, fasta, out, mode, samplers, seed, world, comp="none"):
     env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env["S2S_BLOW5_COMPRESS"] = comp
     args = [sys.executable, str(script), str(fasta), str(out), mode, "1" if samplers else "0", str(seed)]
     if world == 1:
         return [subprocess.run(args, check=True, env=env, timeout=300, capture_output=True, text=True).stdout]
@@ -115,13 +116,18 @@ def _inputs(tmp_path, mode):
     return fasta, script
 
 
-@pytest.mark.parametrize("mode,world,samplers", [("reference", 2, False), ("reference", 3, True), ("read", 2, True)])
-def test_inference_run_n_ranks_equal_one_rank_on_cpu(tmp_path, mode, world, samplers):
+@pytest.mark.parametrize("mode,world,samplers,comp", [("reference", 2, False, "none"), ("reference", 3, True, "zlib+svb-zd"),
+                                                      ("read", 2, True, "none")])
+def test_inference_run_n_ranks_equal_one_rank_on_cpu(tmp_path, mode, world, samplers, comp):
+    """``comp``: pyslow5's default pair (zlib records + svb-zd signal) works in a sharded run too — every rank knows its
+    records' ``start_time`` before it encodes them, so nothing inside a compressed record has to be patched later."""
     from tests.blow5_reader import read_blow5, record_span
     fasta, script = _inputs(tmp_path, mode)
-    _run(tmp_path, script, fasta, tmp_path / "one.blow5", mode, samplers, 21, 1)
-    _run(tmp_path, script, fasta, tmp_path / "many.blow5", mode, samplers, 21, world)
+    _run(tmp_path, script, fasta, tmp_path / "one.blow5", mode, samplers, 21, 1, comp)
+    _run(tmp_path, script, fasta, tmp_path / "many.blow5", mode, samplers, 21, world, comp)
     a, b = read_blow5(str(tmp_path / "one.blow5")), read_blow5(str(tmp_path / "many.blow5"))
+    assert a["record_compression"] == b["record_compression"] == (1 if "zlib" in comp else 0)
+    assert a["signal_compression"] == b["signal_compression"] == (1 if "svb-zd" in comp else 0)
     assert 40 < len(a["records"]) < 90                 # some reads produced no signal and were skipped
     assert a["records"] == b["records"]                # incl. read_number, start_time, offset, median_before
     if samplers:

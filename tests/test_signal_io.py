@@ -1,6 +1,8 @@
 """SLOW5/BLOW5 writer (native libs2s_blow5.so behind seq2squiggle_b200.signal_io) read back with an independent
 parser; record fields as the reference fills them (signal_io.py:104-171)."""
 
+import os
+
 import numpy as np
 import pytest
 
@@ -17,7 +19,7 @@ def _signals(rng, n, empty_at=()):
     return out
 
 
-@pytest.mark.parametrize("comp", ["none", "zlib"])
+@pytest.mark.parametrize("comp", ["none", "zlib", "svb-zd", "zlib+svb-zd"])
 def test_blow5_roundtrip_ideal_mode(tmp_path, comp):
     rng = np.random.default_rng(0)
     prof = get_profile("dna-r10-prom")
@@ -31,8 +33,9 @@ def test_blow5_roundtrip_ideal_mode(tmp_path, comp):
     w.signals = second                       # second flush appends (file exists -> mode 'a')
     w.save()
     f = read_blow5(path)
-    assert f["version"] == (0, 2, 0) and f["num_read_groups"] == 1 and f["signal_compression"] == 0
-    assert f["record_compression"] == (1 if comp == "zlib" else 0)
+    assert f["version"] == (0, 2, 0) and f["num_read_groups"] == 1
+    assert f["signal_compression"] == (1 if "svb-zd" in comp else 0)        # pyslow5's default pair is zlib + svb-zd
+    assert f["record_compression"] == (1 if "zlib" in comp else 0)
     assert f["attrs"]["asic_id"] == "asic_id_0" and f["attrs"]["run_id"] == "run_id_0"
     assert f["attrs"]["flow_cell_id"] == "FAN00000" and f["attrs"]["flow_cell_product_code"] == "FLO-PRO114"
     assert f["attrs"]["experiment_type"] == "genomic_dna" and f["attrs"]["sample_frequency"] == "5000"
@@ -141,3 +144,33 @@ def test_save_flat_equals_dict_save(tmp_path, ideal, preserve):
     assert a[ha:] == b[hb:]
     recs = read_blow5(str(tmp_path / "flat.blow5"))["records"]
     assert [r["read_number"] for r in recs] == [i for i, l in enumerate(np.concatenate([np.diff(o) for _, _, o in batches])) if l > 0]
+
+
+def test_svb_zd_known_answers_and_size(tmp_path):
+    """svb-zd = zigzag-delta + StreamVByte (slow5lib's default signal compression), checked on hand-computed vectors:
+    samples [3, 1, 1, -300, 32767, -32768] -> deltas [3, -2, 0, -301, 33067, -65535] -> zigzag [6, 3, 0, 601, 66134, 131069]
+    -> byte lengths [1, 1, 1, 2 | 3, 3] -> control bytes 0b01000000, 0b00001010 -> 4 + 2 + 11 bytes; and a smooth signal
+    (what a squiggle looks like) shrinks to 1.25 bytes per sample (one data byte + a quarter control byte)."""
+    from seq2squiggle_b200 import _lib
+    import ctypes as C
+    prof = get_profile("dna-r10-prom")
+    x = np.array([3, 1, 1, -300, 32767, -32768], dtype=np.int16)
+    path = str(tmp_path / "k.blow5")
+    w = BLOW5Writer(path, prof, True, "dna-r10-prom", True, record_compression="svb-zd")
+    w.signals = {"kat": x}
+    w.save()
+    data = open(path, "rb").read()
+    blob = bytes([6, 0, 0, 0, 0b01000000, 0b00001010, 6, 3, 0, 0x59, 0x02, 0x56, 0x02, 0x01, 0xFD, 0xFF, 0x01])
+    assert (17).to_bytes(8, "little") + blob in data
+    assert read_blow5(path)["records"][0]["signal"] == x.tolist()
+    rng = np.random.default_rng(5)
+    smooth = np.clip(np.cumsum(rng.integers(-40, 41, size=200000)) // 4 + 600, -32768, 32767).astype(np.int16)
+    sizes = {}
+    for comp in ("none", "svb-zd", "zlib+svb-zd"):
+        p = str(tmp_path / f"s_{comp}.blow5")
+        w = BLOW5Writer(p, prof, True, "dna-r10-prom", True, record_compression=comp)
+        w.signals = {"s": smooth}
+        w.save()
+        sizes[comp] = os.path.getsize(p)
+        assert read_blow5(p)["records"][0]["signal"] == smooth.tolist()
+    assert sizes["svb-zd"] < 0.65 * sizes["none"] and sizes["zlib+svb-zd"] <= sizes["svb-zd"]
