@@ -301,15 +301,46 @@ def run_ours(args):
     e2e_samples, h2d, d2h = sink.samples, pipe_stats["h2d_bytes"], pipe_stats["d2h_bytes"]
     eng.check()
 
+    # ---- the same end-to-end loop with the real writer: every rank appends its records to a BLOW5 file (native writer,
+    # uncompressed records) while the GPU works on the next pieces
+    e2e_w = None
+    if args.writer_e2e:
+        import tempfile
+        from seq2squiggle_b200.signal_io import BLOW5Writer
+        wdir = tempfile.mkdtemp(prefix="s2s_bench_")
+        wpath = os.path.join(wdir, f"rank{rank}.blow5")
+        bw = BLOW5Writer(wpath, get_profile("dna-r10-prom"), False, "dna-r10-prom", False, record_compression="none")
+        model.out_writer = bw
+        model.predict_reads(host_reads[0])          # untimed: creates the file, warms the writer thread
+        model.on_predict_epoch_end()
+        w0 = bw.samples_written
+        barrier()
+        t0w = time.perf_counter()
+        for rd in host_reads[args.warmup:]:
+            model.predict_reads(rd)
+        model.on_predict_epoch_end()
+        torch.cuda.synchronize()
+        barrier()
+        e2e_w = (bw.samples_written - w0, time.perf_counter() - t0w, os.path.getsize(wpath))
+        model.out_writer = sink
+        try:
+            os.remove(wpath)
+            os.rmdir(wdir)
+        except OSError:
+            pass
+
     # ---- per-kernel timing of the dominant kernel (attention) for the roofline, outside the timed region
     kt = kernel_timing(eng, lib, step, args.warmup) if args.precision == "fp16" else None
 
-    stats = torch.tensor([ms, e2e_s, samples, chunks, reads, e2e_samples, launches, h2d, d2h], dtype=torch.float64, device=dev)
+    ew = e2e_w or (0, 0.0, 0)
+    stats = torch.tensor([ms, e2e_s, samples, chunks, reads, e2e_samples, launches, h2d, d2h, ew[0], ew[1], ew[2]],
+                         dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms, e2e_s = float(mx[0]), float(mx[1])
-        samples, chunks, reads, e2e_samples, launches, h2d, d2h = [float(x) for x in sm[2:]]
+        samples, chunks, reads, e2e_samples, launches, h2d, d2h = [float(x) for x in sm[2:9]]
+        ew = (float(sm[9]), float(mx[10]), float(sm[11]))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -330,6 +361,11 @@ def run_ours(args):
             "e2e": {"value": e2e_samples / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": h2d / args.steps / world,
                     "d2h_bytes_per_step": d2h / args.steps / world},
             "gpu_launches": int(launches), "clocks": clk}
+    if e2e_w:
+        line["e2e_with_writer"] = {"value": ew[0] / ew[1], "unit": "samples/s", "file_bytes": ew[2],
+                                   "sink": "one uncompressed BLOW5 file per rank in the temp directory, native writer "
+                                           "thread overlapped with compute (the sharded CLI writes one shared file "
+                                           "the same way: profiles/r02_config5_*gpu.txt)"}
     if args.sharp != 1.0:
         line["config"]["sharp_scale"] = args.sharp
     if kt:
@@ -497,6 +533,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-gpu-eager-baseline", dest="gpu_eager_baseline", action="store_false",
                     help="skip timing the reference's own GPU mode (oracle modules, eager PyTorch, fp16 autocast)")
+    ap.add_argument("--no-writer-e2e", dest="writer_e2e", action="store_false",
+                    help="skip the second end-to-end loop that writes BLOW5 files")
     ap.add_argument("--sharp", type=float, default=1.0,
                     help="scale W_q / W_k of the decoder (trained-like sharp attention: exercises the exact-kernel fallback)")
     args = ap.parse_args()

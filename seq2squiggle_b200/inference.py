@@ -147,6 +147,13 @@ def inference_run(config: dict, saved_weights: str, fasta: str, read_input: bool
 
     rank, world, local = _dist_env()
     out = str(out)
+    if (world > 1 and "CUDA_VISIBLE_DEVICES" not in os.environ and not torch.cuda.is_initialized()
+            and local < torch.cuda.device_count()):      # (device_count() before initialisation asks NVML, not CUDA)
+        # one process per GPU: let each rank see only its own device.  CUDA initialisation enumerates (and sets up) every
+        # visible device; eight ranks doing that for eight GPUs each at the same moment cost ~7 s of the 12 s whole-command
+        # wall time of an 8-GPU run (profiles/r02_config5_8gpu.txt)
+        os.environ["CUDA_VISIBLE_DEVICES"] = str(local)
+        local = 0
     if world > 1:
         # Sharded run (one process per GPU, torchrun): the batches of the read list are dealt to the ranks round-robin and
         # every rank writes its batches straight into the ONE output file, at offsets the ranks hand each other in read

@@ -107,6 +107,9 @@ def main():
         prof = cProfile.Profile()
         prof.enable()
     t0 = time.perf_counter()
+    import torch.cuda as _tc
+    _orig_set_device = _tc.set_device
+    _tc.set_device = timed("torch.cuda.set_device (CUDA initialisation)", _orig_set_device)
     inference.inference_run(config=cfg, saved_weights=ckpt, fasta=fasta, read_input=read_input, n=a.n if a.c < 0 else -1,
                             r=a.r, c=a.c, out=out, profile=profile, dwell_mean=None, dwell_std=0.0, noise_std=2.0,
                             noise_sampling=True, duration_sampling=True, distr="expon", predict_batch_size=1024,
