@@ -770,13 +770,6 @@ __global__ void __launch_bounds__(128, 2) k_tc_qkv_plain(const __grid_constant__
   if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
-__global__ void k_f32_to_f16(const float* __restrict__ x, __half* __restrict__ y, int64_t n4) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 v = reinterpret_cast<const float4*>(x)[i];
-    reinterpret_cast<uint2*>(y)[i] = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
-  }
-}
-
 constexpr int kSmemQkv = 81920;                          // 57 KB used; padded so <= 2 CTAs (TMEM 2 x 256) per SM
 constexpr int kSmemAtt = 6 * kSlab + 96 * 128 + 1024;   // 109 KB -> 2 CTAs / SM
 constexpr int kSmemFfn = 6 * kSlab + 8192 + 1024;       // 105 KB -> 2 CTAs / SM
