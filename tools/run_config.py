@@ -67,6 +67,8 @@ def main():
     ap.add_argument("--c", "--coverage", dest="c", type=int, default=-1)
     ap.add_argument("--r", "--read-length", dest="r", type=int, default=1000)
     ap.add_argument("--genome-len", type=int, default=48502)
+    ap.add_argument("--fasta", default=None, help="use this genome / reads file (e.g. tests/golden/lamda_genome.fasta) "
+                    "instead of writing a synthetic one")
     ap.add_argument("--out", default=None, help="output file (default: a temporary .blow5; /dev/null is not seekable)")
     ap.add_argument("--seed", type=int, default=11)
     ap.add_argument("--profile", action="store_true", help="cProfile the main thread of inference_run")
@@ -82,8 +84,12 @@ def main():
     rng = np.random.default_rng(3)
     fasta = os.path.join(tmp, "input.fasta")
     read_input = a.config == 2
-    with open(fasta, "w") as f:
-        if read_input:   # the 10 read lengths of example/lamda_genome_reads.fasta
+    if a.fasta:
+        fasta = a.fasta
+    with open(os.devnull if a.fasta else fasta, "w") as f:
+        if a.fasta:
+            pass
+        elif read_input:   # the 10 read lengths of example/lamda_genome_reads.fasta
             for i, ln in enumerate([2843, 10510, 8487, 2207, 11936, 4407, 1434, 2449, 14971, 11072]):
                 f.write(f">read{i}\n" + rng.choice(list("ACGT"), ln).astype("U1").tobytes().decode("utf-32-le") + "\n")
         else:
