@@ -169,6 +169,20 @@ def inference_run(config: dict, saved_weights: str, fasta: str, read_input: bool
         saved_weights = get_saved_weights(profile)
 
     local = local % max(torch.cuda.device_count(), 1)   # more ranks than GPUs (tests): ranks share devices
+    plan_state = None
+    if world > 1:
+        # CUDA initialisation of N processes at once takes seconds (5-6 s for eight, whatever each of them may see); the
+        # batch plan needs no GPU (genome preprocessing + lengths-only replay of the sampler: 1-2 s), so it runs meanwhile
+        import threading
+        import torch.distributed as dist
+        init = threading.Thread(target=torch.cuda.set_device, args=(local,), daemon=True)
+        init.start()
+        if not dist.is_initialized():
+            dist.init_process_group("gloo")      # control plane only: barriers around the shared file
+        plan_state = get_reads_batches(fasta, read_input, n, r, c, config, distr,
+                                       seed, profile, min_read_len, rank, world, plan_batches, chunks_of_read,
+                                       cheap_names=not preserve_read_ids)
+        init.join()
     torch.cuda.set_device(local)
     load_model = seq2squiggle.load_from_checkpoint(
         checkpoint_path=saved_weights, out_writer=writer, dwell_mean=dwell_mean, dwell_std=dwell_std,
@@ -184,11 +198,7 @@ def inference_run(config: dict, saved_weights: str, fasta: str, read_input: bool
     if world > 1:
         import torch.distributed as dist
         from .signal_io import SharedOrder
-        if not dist.is_initialized():
-            dist.init_process_group("gloo")      # control plane only: barriers around the shared file
-        reads, plan, counts = get_reads_batches(
-            fasta, read_input, n, r, c, config, distr, seed, profile, min_read_len, rank, world, plan_batches,
-            chunks_of_read, cheap_names=not preserve_read_ids)
+        reads, plan, counts = plan_state
         chunk_cum = np.concatenate([[0], np.cumsum(counts)])
         mine = list(range(rank, len(plan), world))
         logger.info(f"rank {rank}/{world}: {len(mine)} of {len(plan)} batches, {len(counts)} reads in the run")
