@@ -26,7 +26,7 @@ struct TcBuffers {
   __half* o16 = nullptr;    // [rows,64]  attention output (A operand of fc)
   __half* xe16 = nullptr;   // encoder: [chunks*16 (padded to 128), 64] fp16 residual-stream copy
   __half* oe16 = nullptr;   // encoder attention output
-  int32_t* flags = nullptr; // [0] = number of flagged units, [1..2*chunks] = per-unit overflow flags of k_tc_attn2
+  int32_t* flags = nullptr; // [0] = number of flagged units, [1..2*chunks] = per-unit overflow flags of k_tc_attn3
 };
 
 void tc_carve(TcBuffers& b, char* base, int64_t& off, int64_t batch_chunks);

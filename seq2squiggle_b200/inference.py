@@ -192,8 +192,8 @@ def inference_run(config: dict, saved_weights: str, fasta: str, read_input: bool
     check_model(load_model.hparams.config, config)
 
     # reads are sampled lazily, batch by batch, while the GPU works on the previous batches (the sampler is
-    # sequential Python); a sharded multi-process run first replays the sampler for the read lengths alone to
-    # balance the ranks by chunk count, then materialises only its own reads (reads.get_reads_shard)
+    # sequential Python); a sharded multi-process run has replayed the sampler for the read lengths alone (above), cut the
+    # list into batches and materialises only its own batches (reads.get_reads_batches)
     k = config["seq_kmer"]
     if world > 1:
         import torch.distributed as dist
