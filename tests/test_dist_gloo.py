@@ -33,7 +33,7 @@ RUN_WORKER = textwrap.dedent("""
     from seq2squiggle_b200.checkpoint import DEFAULT_CONFIG
     from seq2squiggle_b200.cli import set_seeds
 
-    model_mod.PIPE_CHUNKS = 300          # small batches: about a dozen per run, dealt round-robin to the ranks
+    model_mod.PIPE_CHUNKS = int(os.environ.get("S2S_TEST_PIPE", 300))   # small batches: about a dozen per run, round-robin
 
     class FakeModel:
         '''What inference_run touches of seq2squiggle: load_from_checkpoint, hparams.config, chunks_done, predict_reads,
@@ -138,6 +138,19 @@ def test_inference_run_n_ranks_equal_one_rank_on_cpu(tmp_path, mode, world, samp
         blobs.append(open(tmp_path / name, "rb").read()[lo:])
     assert blobs[0] == blobs[1]
     # nothing but the output is left behind: no part files, no hand-over table
+    assert sorted(os.listdir(tmp_path)) == ["in.fasta", "many.blow5", "one.blow5", "run_worker.py"]
+
+
+def test_more_ranks_than_batches(tmp_path, monkeypatch):
+    """A run that is one batch long under three ranks: ranks 1 and 2 own nothing, open the shared file, write nothing and
+    leave; the file is the single-process file."""
+    from tests.blow5_reader import read_blow5, record_span
+    monkeypatch.setenv("S2S_TEST_PIPE", "1000000")
+    fasta, script = _inputs(tmp_path, "reference")
+    _run(tmp_path, script, fasta, tmp_path / "one.blow5", "reference", True, 21, 1)
+    _run(tmp_path, script, fasta, tmp_path / "many.blow5", "reference", True, 21, 3)
+    a, b = read_blow5(str(tmp_path / "one.blow5")), read_blow5(str(tmp_path / "many.blow5"))
+    assert a["records"] == b["records"] and len(a["records"]) > 40
     assert sorted(os.listdir(tmp_path)) == ["in.fasta", "many.blow5", "one.blow5", "run_worker.py"]
 
 
