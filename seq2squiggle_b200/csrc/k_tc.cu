@@ -377,6 +377,41 @@ __global__ void __launch_bounds__(128, 2) k_tc_attn(const __grid_constant__ CUte
   if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
+// Fused output epilogue of the last decoder block (modules.py:140-141, model.py:221-240): p = ReLU(out_linear), pA = 165 p,
+// Philox noise where pA != 0, clamp at 0 — written ONCE as fp32 pA, 250 positions per chunk, plus the chunk's count of
+// non-zero samples (what the zero-strip compaction scans); pad rows 250..255 emit nothing.  y: the thread's LayerNorm-2 row.
+__device__ __forceinline__ void out_head_epilogue(const float (&y)[64], const FfnParams& P, const OutEpi& E, int64_t row) {
+  float acc = P.bout;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) acc = fmaf(y[i], P.wout[i], acc);
+  const int64_t c = row >> 8;
+  const int t = (int)(row & 255);
+  bool nz = false;
+  if (t < S2S_L_DEC) {
+    const int64_t idx = c * S2S_L_DEC + t;
+    const float p = fmaxf(acc, 0.f);
+    if (E.p_tap) E.p_tap[idx] = p;
+    float v_pa = p * E.scaling;
+    if (E.o.noise_mode != S2S_NOISE_OFF && v_pa != 0.f) {
+      const Philox ph(E.o.seed);
+      const uint64_t gc = E.o.chunk_id_base + (uint64_t)c;
+      const uint4 rr = ph((uint32_t)gc, (uint32_t)(gc >> 32), (uint32_t)t, kStreamNoiseTc);
+      const float z = box_muller(rr.x, rr.y).x;
+      const float sd = E.o.noise_mode == S2S_NOISE_SAMPLER
+                           ? fmaxf(E.sigma_ext[idx], E.o.min_noise) * E.o.noise_std * E.scaling   // model.py:228-230
+                           : E.o.noise_std;                                                        // model.py:236
+      v_pa += z * sd;
+    }
+    v_pa = fmaxf(v_pa, 0.f);
+    E.pa[idx] = v_pa;
+    nz = v_pa != 0.f;
+  }
+  if (E.counts) {   // a warp's 32 rows belong to one chunk (256 rows per chunk)
+    const unsigned m = __ballot_sync(0xffffffffu, nz);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(E.counts + c, __popc(m));
+  }
+}
+
 #if defined(S2S_PHASE_TIMING) && S2S_PHASE_TIMING == 2
 // FFN phase timing: thread 0 (issues the MMAs) -> g_phase[0..7], thread 32 (pure epilogue thread) -> g_phase[8..15]
 #define PHF_DECL const int phf_base = threadIdx.x == 0 ? 0 : 8; const bool phf_on = threadIdx.x == 0 || threadIdx.x == 32; \
@@ -635,40 +670,7 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
     } else {
       layernorm_store<kRes32, !kOutHead>(y, P.g2, P.be2, x32 + row * 64, x16 + row * 64);
     }
-    if (kOutHead) {
-      // Fused output epilogue (modules.py:140-141, model.py:221-240): p = ReLU(out_linear), pA = 165 p, Philox noise
-      // where pA != 0, clamp at 0 — written ONCE as fp32 pA, 250 positions per chunk, plus the chunk's count of non-zero
-      // samples (what the zero-strip compaction scans); pad rows 250..255 emit nothing.
-      float acc = P.bout;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) acc = fmaf(y[i], P.wout[i], acc);
-      const int64_t c = row >> 8;
-      const int t = (int)(row & 255);
-      bool nz = false;
-      if (t < S2S_L_DEC) {
-        const int64_t idx = c * S2S_L_DEC + t;
-        const float p = fmaxf(acc, 0.f);
-        if (E.p_tap) E.p_tap[idx] = p;
-        float v_pa = p * E.scaling;
-        if (E.o.noise_mode != S2S_NOISE_OFF && v_pa != 0.f) {
-          const Philox ph(E.o.seed);
-          const uint64_t gc = E.o.chunk_id_base + (uint64_t)c;
-          const uint4 rr = ph((uint32_t)gc, (uint32_t)(gc >> 32), (uint32_t)t, kStreamNoiseTc);
-          const float z = box_muller(rr.x, rr.y).x;
-          const float sd = E.o.noise_mode == S2S_NOISE_SAMPLER
-                               ? fmaxf(E.sigma_ext[idx], E.o.min_noise) * E.o.noise_std * E.scaling   // model.py:228-230
-                               : E.o.noise_std;                                                        // model.py:236
-          v_pa += z * sd;
-        }
-        v_pa = fmaxf(v_pa, 0.f);
-        E.pa[idx] = v_pa;
-        nz = v_pa != 0.f;
-      }
-      if (E.counts) {   // a warp's 32 rows belong to one chunk (256 rows per chunk)
-        const unsigned m = __ballot_sync(0xffffffffu, nz);
-        if ((tid & 31) == 0 && m) atomicAdd(E.counts + c, __popc(m));
-      }
-    }
+    if (kOutHead) out_head_epilogue(y, P, E, row);
     __syncthreads();  // all TMEM reads are done before the next tile's MMA overwrites the accumulators
     tcgen05_fence_after();
     if (kTmaStore && tid == 0) {
@@ -682,6 +684,8 @@ __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CU
   __syncthreads();
   if (warp == 0) tmem_dealloc<256>(tmem);
 }
+
+#include "k_tc_ffn4.cuh"
 
 // =================================================================================================
 // ENC-QKV: qkv[rows,192] (fp32) = X Wqkv^T + b for the encoder rows (16 per chunk; the 16-key attention itself
@@ -810,6 +814,8 @@ int tc_init(TcState& s, const DevWeights& w, int device) {
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn4));
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn4));
   (void)w;
   S2S_CUDA_OK(cudaMalloc(&s.d_status, 256));
   S2S_CUDA_OK(cudaMemset(s.d_status, 0, 256));
@@ -872,7 +878,17 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, const OutEpi
     S2S_LAUNCH_CHECK();
     prof_end(s, PROF_ATTN, e0, n_chunks, st);
     e0 = prof_begin(s, st);
-    if (l + 1 < w.cfg.decoder_layers)
+    // one 512-thread CTA per SM running four tile pipelines over one copy of the weights (k_tc_ffn4.cuh);
+    // S2S_FFN_VER=2 selects the two-CTAs-per-SM kernel it replaced (A/B measurements, profiles/r02_ffn4_ab.txt)
+    static const int ffn_ver = getenv("S2S_FFN_VER") ? atoi(getenv("S2S_FFN_VER")) : 4;
+    const bool last = l + 1 == w.cfg.decoder_layers;
+    if (ffn_ver != 2) {
+      const int g4 = n_tiles < s.sm_count ? n_tiles : s.sm_count;
+      if (!last)
+        k_tc_fc_ffn4<false><<<g4, kFfn4Threads, kSmemFfn4, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, b.x16, epi, n_tiles, s.d_status);
+      else
+        k_tc_fc_ffn4<true><<<g4, kFfn4Threads, kSmemFfn4, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, b.x16, epi, n_tiles, s.d_status);
+    } else if (!last)
       k_tc_fc_ffn<false, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, nullptr, b.x16, epi,
                                                              n_tiles, s.d_status);
     else
