@@ -163,7 +163,13 @@ __global__ void __launch_bounds__(kFfn4Threads, 1) k_tc_fc_ffn4(const __grid_con
         if (kTmaStore && it > 0) tma_store_wait_read();
         mbar_arrive_expect_tx(&bars[F4Bars::O + 2 * p + (buf ^ 1)], kSlab);
         tma_load_2d(sAp + (buf ^ 1) * kSlab, &tmA, &bars[F4Bars::O + 2 * p + (buf ^ 1)], 0, (tile + stride) * 128);
+        // the next tile's residual rows (x16 = the tensor tmXout describes): into L2 now, so that the row loads a tile
+        // later are not DRAM round trips
+        tma_prefetch_l2_2d(&tmXout, 0, (tile + stride) * 128);
       }
+      uint32_t xr[4][8];   // first residual (the block input, fp16): four 32-byte sectors of the thread's row, in flight
+#pragma unroll         // while the fc MMA is issued and runs
+      for (int i = 0; i < 4; ++i) ldg_256(x16 + row * 64 + 16 * i, xr[i]);
       if (issuer) {   // attention output projection: ACC = O Wfc^T (the previous tile's D2 was read before its closing sync)
         wait_a(BAR(F4Bars::O + 2 * p + buf), ((uint32_t)it >> 1) & 1u, kErrFfnLoad);
         tcgen05_fence_after();
@@ -175,23 +181,14 @@ __global__ void __launch_bounds__(kFfn4Threads, 1) k_tc_fc_ffn4(const __grid_con
         }
         __syncwarp();
       }
-      if (it + 1 < n_it)   // the next tile's residual row: into L2 now, so that its load a tile later is not a DRAM round trip
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(x16 + (row + (int64_t)stride * 128) * 64));
       float y[64];
-      {  // first residual (the block input, fp16), while the fc MMA runs
-        const uint4* rp = reinterpret_cast<const uint4*>(x16 + row * 64);
-        uint4 xr[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) xr[i] = rp[i];
+      for (int i = 0; i < 4; ++i) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t w4[4] = {xr[i].x, xr[i].y, xr[i].z, xr[i].w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[j]));
-            y[8 * i + 2 * j] = f.x;
-            y[8 * i + 2 * j + 1] = f.y;
-          }
+        for (int j = 0; j < 8; ++j) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&xr[i][j]));
+          y[16 * i + 2 * j] = f.x;
+          y[16 * i + 2 * j + 1] = f.y;
         }
       }
       wait_a(BAR(F4Bars::FC + p), ph, kErrFcMma);
