@@ -400,9 +400,10 @@ def run_ours(args):
         if "ffn" in kt:
             f = kt["ffn"]
             ach = FFN_FLOP_PER_CHUNK_LAYER * f["chunks_per_launch"] / (f["ms_per_launch"] * 1e-3) / 1e12
-            kernels.append({"kernel": "k_tc_fc_ffn (fc + LN + FFN + LN; last layer: + out_linear, x165, noise, clamp, count)",
+            gbs = FFN_BYTES_PER_CHUNK_LAYER * f["chunks_per_launch"] / (f["ms_per_launch"] * 1e-3) / 1e9
+            kernels.append({"kernel": "k_tc_fc_ffn4 (fc + LN + FFN + LN; last layer: + out_linear, x165, noise, clamp, count)",
                             "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                            "hbm_gbs": FFN_BYTES_PER_CHUNK_LAYER * f["chunks_per_launch"] / (f["ms_per_launch"] * 1e-3) / 1e9,
+                            "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak,
                             "ms_per_launch": f["ms_per_launch"], "launches_timed": f["launches"], "share_of_step": f["share"]})
         if "length_regulate" in kt:
             f = kt["length_regulate"]

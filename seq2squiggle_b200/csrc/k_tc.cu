@@ -452,6 +452,8 @@ __global__ void k_attn_gate(const int* __restrict__ hint, int probe, int n_units
 //         HBM traffic instead of 768.  LayerNorm, both residual adds and the accumulators stay fp32 in registers/TMEM.
 // kOutHead: last decoder block: p = ReLU(out_linear(LN2 output)) (modules.py:140-141) from the fp32 registers, one
 //         float per row; the block output itself is not written at all.
+// Since round 2 only the encoder (<true, false>) is launched through this kernel: the decoder blocks run k_tc_fc_ffn4
+// (k_tc_ffn4.cuh, four tiles in flight per SM), which shares out_head_epilogue() and the parameter block with it.
 template <bool kRes32, bool kOutHead>
 __global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmWfc,
@@ -812,8 +814,6 @@ int tc_init(TcState& s, const DevWeights& w, int device) {
   if (const char* env = getenv("S2S_ATTN_EXACT")) s.attn_exact = atoi(env) != 0;   // tests: the exact kernel on its own
   if (const char* env = getenv("S2S_ATTN_V1")) s.attn_exact = atoi(env) != 0;      // (older spelling)
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
-  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
-  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn4));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn4));
   (void)w;
@@ -841,7 +841,6 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, const OutEpi
     set_error("cuTensorMapEncodeTiled failed for an activation tensor");
     return -1;
   }
-  const int grid2 = n_tiles < 2 * s.sm_count ? n_tiles : 2 * s.sm_count;
   const int n_units = (int)(2 * n_chunks);
   int32_t* d_flags = b.flags;  // [0] = number of flagged units, [1..] = per-unit overflow flags (workspace)
   const int grid_att = n_units < 2 * s.sm_count ? n_units : 2 * s.sm_count;  // even stride: a CTA keeps its head group
@@ -878,22 +877,12 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, const OutEpi
     S2S_LAUNCH_CHECK();
     prof_end(s, PROF_ATTN, e0, n_chunks, st);
     e0 = prof_begin(s, st);
-    // one 512-thread CTA per SM running four tile pipelines over one copy of the weights (k_tc_ffn4.cuh);
-    // S2S_FFN_VER=2 selects the two-CTAs-per-SM kernel it replaced (A/B measurements, profiles/r02_ffn4_ab.txt)
-    static const int ffn_ver = getenv("S2S_FFN_VER") ? atoi(getenv("S2S_FFN_VER")) : 4;
-    const bool last = l + 1 == w.cfg.decoder_layers;
-    if (ffn_ver != 2) {
-      const int g4 = n_tiles < s.sm_count ? n_tiles : s.sm_count;
-      if (!last)
-        k_tc_fc_ffn4<false><<<g4, kFfn4Threads, kSmemFfn4, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, b.x16, epi, n_tiles, s.d_status);
-      else
-        k_tc_fc_ffn4<true><<<g4, kFfn4Threads, kSmemFfn4, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, b.x16, epi, n_tiles, s.d_status);
-    } else if (!last)
-      k_tc_fc_ffn<false, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, nullptr, b.x16, epi,
-                                                             n_tiles, s.d_status);
+    // one 512-thread CTA per SM running four tile pipelines over one copy of the weights (k_tc_ffn4.cuh)
+    const int g4 = n_tiles < s.sm_count ? n_tiles : s.sm_count;
+    if (l + 1 < w.cfg.decoder_layers)
+      k_tc_fc_ffn4<false><<<g4, kFfn4Threads, kSmemFfn4, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, b.x16, epi, n_tiles, s.d_status);
     else
-      k_tc_fc_ffn<false, true><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, nullptr, b.x16, epi,
-                                                            n_tiles, s.d_status);
+      k_tc_fc_ffn4<true><<<g4, kFfn4Threads, kSmemFfn4, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, b.x16, epi, n_tiles, s.d_status);
     S2S_LAUNCH_CHECK();
     prof_end(s, PROF_FFN, e0, n_chunks, st);
   }

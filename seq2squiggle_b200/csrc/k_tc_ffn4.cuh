@@ -1,28 +1,35 @@
 // k_tc_fc_ffn4 — decoder fc + LN + FFN + LN with FOUR tiles in flight per SM (included by k_tc.cu inside
 // namespace s2s::{anonymous}).
 //
-// layers.py:82-86, 108-113 for 128-row tiles of the decoder's fp16 residual stream, same arithmetic as k_tc_fc_ffn
-// (fp16 operands, fp32 accumulate / LayerNorm / residual adds).  k_tc_fc_ffn runs two 128-thread CTAs per SM because a tile
-// needs 256 TMEM columns (the 256-wide hidden layer) and 105 KB of shared memory (a private copy of the weights): two tiles
-// in flight, 0.365 of the tensor peak, and one tile alone on an SM takes 8.3 k clk against 5.1 k per tile with two
-// (profiles/r02_experiments_not_kept.txt): the kernel is bound by how many independent tiles cover each other's MMA,
-// TMEM and LayerNorm latencies.  Here ONE 512-thread CTA per SM runs four tile pipelines over ONE copy of the weights:
+// layers.py:82-86, 108-113 for 128-row tiles of the decoder's fp16 residual stream (fp16 operands, fp32 accumulate /
+// LayerNorm / residual adds).  The round-1 kernel k_tc_fc_ffn ran two 128-thread CTAs per SM (256 TMEM columns and a private
+// 105 KB copy of the weights per tile): two tiles in flight, 0.365 of the tensor peak, and one tile alone on an SM takes
+// 8.3 k clk against 5.1 k per tile with two (profiles/r02_experiments_not_kept.txt) — the kernel is bound by how many
+// independent tiles cover each other's MMA, TMEM and memory latencies.  Here ONE 512-thread CTA per SM runs four tile
+// pipelines over ONE copy of the weights:
 //   warpgroup p = warps 4p..4p+3 (thread = row of the pipeline's current tile): residual, LayerNorms, ReLU, output; the
 //   pipeline's tcgen05.mma are issued by one elected lane of warp 4p with uniform descriptors (dedicated MMA warps cost
-//   the epilogue threads a third of their registers: 96 instead of 128, and the spills that followed made it slower).
+//   the row threads a quarter of their registers: 96 instead of 128, and the spills that followed made it slower).
 // The hidden layer is processed in four 64-column quarters so that a pipeline needs 128 TMEM columns:
-//   [128p, 128p+64)    ACC: fc accumulator, later D2 (accumulated over the four quarters)
-//   [128p+64, 128p+128) D1 quarter (fp32) -> H quarter (packed fp16 over its first 32 columns, A operand of W2)
-// Per tile: fc -> epilogue 1 (residual + LN1, fp16 Y into the O tile's buffer) -> 4 x [W1 quarter -> ReLU/pack -> W2 quarter]
-// -> epilogue 2 (residual + LN2 -> TMA store, or the fused output epilogue of the last block).
-// Shared memory: W1 32 KB | W2 32 KB | Wfc 8 KB | 4 pipelines x 2 x 16 KB (O / Y / output rows, double-buffered) = 200 KB.
+//   [128p, 128p+64)    ACC: fc accumulator, later D2 (b2 + the four quarters)
+//   [128p+64, 128p+128) D1 quarter (fp32) -> H quarter (ReLU, packed fp16 over its first 32 columns, A operand of W2)
+// Per tile: fc -> residual + LN1 (fp16 Y over the O tile's buffer) -> 4 x [W1 quarter -> ReLU/pack -> W2 quarter]
+// -> residual + LN2 -> TMA store, or the fused output epilogue of the last block.
+// Instruction diet (the row threads' issue slots are the second bound after latency):
+//   * every bias goes through the tensor core: one extra K = 16 MMA of a constant (1, 1, 0 ...) A tile against a bias B
+//     tile (bias as fp16 hi + lo, exact to ~22 bits in the fp32 accumulator) instead of 384 FADD per row;
+//   * LayerNorm in one pass (sum and sum of squares while the accumulator is added) and two FFMA per element;
+//   * the residual row by four 256-bit loads issued ahead of the fc MMA, its tile prefetched into L2 by TMA a tile earlier.
+// Shared memory: W1 32 KB | W2 32 KB | Wfc 8 KB | 4 pipelines x 2 x 16 KB (O / Y / output rows, double-buffered) | ones +
+// bias tile 16 KB = 216 KB.  Measured: 1.142 ms (k_tc_fc_ffn) -> 0.81 ms per 32768-chunk layer, 0.52 of the measured bf16
+// tensor peak at 60 % of the HBM copy peak (3.2 GB per launch); profiles/r02_ffn4_ncu.txt.
 #pragma once
 
 constexpr int kFfn4Threads = 4 * 128;
 constexpr int kSmemFfn4 = 4 * kSlab + 8192 + 8 * kSlab + kSlab + 1024;
 
 struct F4Bars {  // per pipeline p: index = base + p (O: base + 2 p + buf)
-  enum { W = 0, O = 1, FC = 9, Y = 13, M1 = 17, H = 21, M2 = 25, D2 = 29, ACCFREE = 33, COUNT = 37 };
+  enum { W = 0, O = 1, FC = 9, M1 = 13, M2 = 17, D2 = 21, COUNT = 25 };
 };
 
 // LayerNorm over a 64-wide row held in registers, from its running sum and sum of squares (one pass: the rows are O(1)
@@ -60,7 +67,7 @@ __global__ void __launch_bounds__(kFfn4Threads, 1) k_tc_fc_ffn4(const __grid_con
   //   K-step 3, rows 0..63: bfc ; rows 64..127: b2
   // each bias as fp16 (hi, lo) in k = 0, 1, so the product 1*hi + 1*lo carries it to ~22 bits into the fp32 accumulator.
   uint8_t* sB = smem + 4 * kSlab + 8192 + 8 * kSlab;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   if (tid == 0) s_go = (*status == 0);
   for (int i = tid; i < (int)(kSlab / 16); i += kFfn4Threads) reinterpret_cast<uint4*>(sB)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -85,7 +92,6 @@ __global__ void __launch_bounds__(kFfn4Threads, 1) k_tc_fc_ffn4(const __grid_con
       mbar_init(&bars[F4Bars::O + 2 * p], 1); mbar_init(&bars[F4Bars::O + 2 * p + 1], 1);
       mbar_init(&bars[F4Bars::FC + p], 1); mbar_init(&bars[F4Bars::M1 + p], 1); mbar_init(&bars[F4Bars::M2 + p], 1);
       mbar_init(&bars[F4Bars::D2 + p], 1);
-      mbar_init(&bars[F4Bars::Y + p], 4); mbar_init(&bars[F4Bars::H + p], 4); mbar_init(&bars[F4Bars::ACCFREE + p], 4);
     }
     fence_mbar_init();
     s_abort = 0;
@@ -107,10 +113,6 @@ __global__ void __launch_bounds__(kFfn4Threads, 1) k_tc_fc_ffn4(const __grid_con
     sts_u32(abort_a, 1u);
     atomicExch(status, code);
     return false;
-  };
-  auto warp_arrive_a = [&](uint32_t a) {
-    __syncwarp();
-    if (lane == 0) mbar_arrive_a(a);
   };
   if (tmem != 0u) {   // the one CTA of the SM owns all 512 columns: TMEM operands below are immediates
     if (tid == 0) atomicExch(status, kErrFfnLoad);
