@@ -776,6 +776,8 @@ __global__ void __launch_bounds__(128, 2) k_tc_qkv_plain(const __grid_constant__
   if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
+#include "k_tc_enc.cuh"
+
 constexpr int kSmemQkv = 81920;                          // 57 KB used; padded so <= 2 CTAs (TMEM 2 x 256) per SM
 constexpr int kSmemAtt = 6 * kSlab + 96 * 128 + 1024;   // 109 KB -> 2 CTAs / SM
 constexpr int kSmemFfn = 6 * kSlab + 8192 + 1024;       // 105 KB -> 2 CTAs / SM
@@ -809,6 +811,7 @@ int tc_init(TcState& s, const DevWeights& w, int device) {
     return -1;
   }
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_qkv_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemQkv));
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_enc_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEncAttn));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn3, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt3));
   if (const char* env = getenv("S2S_ATTN_EXACT")) s.attn_exact = atoi(env) != 0;   // tests: the exact kernel on its own
@@ -919,10 +922,16 @@ int tc_encoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, 
       set_error("cuTensorMapEncodeTiled failed for a weight tensor");
       return -1;
     }
-    __half* qkv16 = reinterpret_cast<__half*>(qkv32);   // the fp32 scratch of the SIMT path, used as fp16 here
-    k_tc_qkv_plain<<<grid2, 128, kSmemQkv, st>>>(tmX, tmWqkv, bl.bqkv, qkv16, (int64_t)rows, s.d_status);
-    S2S_LAUNCH_CHECK();
-    if (launch_attention_enc_f16(qkv16, o16, n_chunks, st)) return -1;
+    static const bool enc_fused = !(getenv("S2S_ENC_FUSED") && atoi(getenv("S2S_ENC_FUSED")) == 0);   // A/B switch
+    if (enc_fused) {
+      k_tc_enc_attn<<<grid2, 256, kSmemEncAttn, st>>>(tmX, tmWqkv, bl.bqkv, o16, (int64_t)rows, s.d_status);
+      S2S_LAUNCH_CHECK();
+    } else {
+      __half* qkv16 = reinterpret_cast<__half*>(qkv32);   // the fp32 scratch of the SIMT path, used as fp16 here
+      k_tc_qkv_plain<<<grid2, 128, kSmemQkv, st>>>(tmX, tmWqkv, bl.bqkv, qkv16, (int64_t)rows, s.d_status);
+      S2S_LAUNCH_CHECK();
+      if (launch_attention_enc_f16(qkv16, o16, n_chunks, st)) return -1;
+    }
     k_tc_fc_ffn<true, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, x32, x16, OutEpi{}, n_tiles,
                                                            s.d_status);
     S2S_LAUNCH_CHECK();

@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(kFfn4Threads, 1) k_tc_fc_ffn4(const __grid_con
       const int buf = it & 1;
       const uint32_t ph = (uint32_t)it & 1u;
       uint8_t* sAb = sAp + buf * kSlab;
+      const uint32_t sAb_a = smem_u32(sAb);
       const uint64_t dA = dAp + (uint64_t)((buf * kSlab) >> 4);
       const int64_t row = (int64_t)tile * 128 + r;
       if (r == 0 && it + 1 < n_it) {   // the other buffer: its last reader is the TMA store of the previous tile's rows
@@ -211,9 +212,9 @@ __global__ void __launch_bounds__(kFfn4Threads, 1) k_tc_fc_ffn4(const __grid_con
       ln_apply(y, sum, sq, P.g1, P.be1);   // LayerNorm 1 (slf_attn.layer_norm); Y stays in registers
 #pragma unroll
       for (int c = 0; c < 8; ++c)   // fp16 copy -> swizzled A tile over the O tile
-        *reinterpret_cast<uint4*>(sAb + sw128_offset(r, c)) =
+        sts_u4(sAb_a + sw128_offset(r, c),
             make_uint4(pack_half2(y[8 * c], y[8 * c + 1]), pack_half2(y[8 * c + 2], y[8 * c + 3]),
-                       pack_half2(y[8 * c + 4], y[8 * c + 5]), pack_half2(y[8 * c + 6], y[8 * c + 7]));
+                       pack_half2(y[8 * c + 4], y[8 * c + 5]), pack_half2(y[8 * c + 6], y[8 * c + 7])));
       fence_proxy_async_smem();
       tcgen05_fence_before();
       wg_sync();   // Y is in shared memory, the fc accumulator has been read
@@ -283,9 +284,9 @@ __global__ void __launch_bounds__(kFfn4Threads, 1) k_tc_fc_ffn4(const __grid_con
       if constexpr (kTmaStore) {
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(sAb + sw128_offset(r, c)) =
+          sts_u4(sAb_a + sw128_offset(r, c),
               make_uint4(pack_half2(y[8 * c], y[8 * c + 1]), pack_half2(y[8 * c + 2], y[8 * c + 3]),
-                         pack_half2(y[8 * c + 4], y[8 * c + 5]), pack_half2(y[8 * c + 6], y[8 * c + 7]));
+                         pack_half2(y[8 * c + 4], y[8 * c + 5]), pack_half2(y[8 * c + 6], y[8 * c + 7])));
         fence_proxy_async_smem();
       } else {
         out_head_epilogue(y, P, E, row);
