@@ -178,29 +178,14 @@ __global__ void __launch_bounds__(256) k_attention_dec_f32(const float* __restri
   *reinterpret_cast<float4*>(op + 4) = make_float4(o[4] * inv, o[5] * inv, o[6] * inv, o[7] * inv);
 }
 
-// Encoder length (16 keys): one CTA of 128 threads per chunk, thread = (head, query).
-template <typename OutT, typename InT = float>
-__global__ void __launch_bounds__(128) k_attention_enc_f32(const InT* __restrict__ qkv, OutT* __restrict__ out) {
+// Encoder length (16 keys), fp32 path: one CTA of 128 threads per chunk, thread = (head, query).  (The fp16 path does this
+// inside k_tc_enc_attn, csrc/k_tc_enc.cuh.)
+__global__ void __launch_bounds__(128) k_attention_enc_f32(const float* __restrict__ qkv, float* __restrict__ out) {
   __shared__ __align__(16) float s[S2S_L_ENC][192];
   const int64_t c = blockIdx.x;
   const int tid = threadIdx.x;
-  if constexpr (sizeof(InT) == 4) {
-    const float4* src = reinterpret_cast<const float4*>(qkv + c * S2S_L_ENC * 192);
-    for (int i = tid; i < S2S_L_ENC * 192 / 4; i += 128) reinterpret_cast<float4*>(&s[0][0])[i] = src[i];
-  } else {  // fp16 q|k|v from the tensor-core projection: 16-byte loads of 8 values, widened into the fp32 tile
-    const uint4* src = reinterpret_cast<const uint4*>(qkv + c * S2S_L_ENC * 192);
-    for (int i = tid; i < S2S_L_ENC * 192 / 8; i += 128) {
-      const uint4 v = src[i];
-      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-      float* dst = &s[0][0] + 8 * i;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[j]));
-        dst[2 * j] = f.x;
-        dst[2 * j + 1] = f.y;
-      }
-    }
-  }
+  const float4* src = reinterpret_cast<const float4*>(qkv + c * S2S_L_ENC * 192);
+  for (int i = tid; i < S2S_L_ENC * 192 / 4; i += 128) reinterpret_cast<float4*>(&s[0][0])[i] = src[i];
   __syncthreads();
   const int h = tid >> 4, qi = tid & 15;
   const float scale = 0.35355339059327373f;
@@ -225,22 +210,15 @@ __global__ void __launch_bounds__(128) k_attention_enc_f32(const InT* __restrict
     for (int d = 0; d < 8; ++d) o[d] = fmaf(p, s[j][128 + 8 * h + d], o[d]);
   }
   const float inv = 1.0f / sum;
-  OutT* op = out + (c * S2S_L_ENC + qi) * 64 + 8 * h;
-  if constexpr (sizeof(OutT) == 4) {
-    *reinterpret_cast<float4*>(op) = make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
-    *reinterpret_cast<float4*>(op + 4) = make_float4(o[4] * inv, o[5] * inv, o[6] * inv, o[7] * inv);
-  } else {
-    __half2 h0 = __floats2half2_rn(o[0] * inv, o[1] * inv), h1 = __floats2half2_rn(o[2] * inv, o[3] * inv);
-    __half2 h2 = __floats2half2_rn(o[4] * inv, o[5] * inv), h3 = __floats2half2_rn(o[6] * inv, o[7] * inv);
-    *reinterpret_cast<uint4*>(op) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
-  }
+  float* op = out + (c * S2S_L_ENC + qi) * 64 + 8 * h;
+  *reinterpret_cast<float4*>(op) = make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
+  *reinterpret_cast<float4*>(op + 4) = make_float4(o[4] * inv, o[5] * inv, o[6] * inv, o[7] * inv);
 }
 
 int launch_attention_f32(const float* qkv, float* out, int64_t n_chunks, int L, int rows_per_chunk, cudaStream_t st) {
   if (n_chunks == 0) return 0;
   if (L == S2S_L_ENC && rows_per_chunk == S2S_L_ENC) {
-    k_attention_enc_f32<float><<<(unsigned)n_chunks, 128, 0, st>>>(qkv, out);
+    k_attention_enc_f32<<<(unsigned)n_chunks, 128, 0, st>>>(qkv, out);
   } else if (L == S2S_L_DEC && rows_per_chunk == S2S_L_DEC_PAD) {
     k_attention_dec_f32<<<(unsigned)(n_chunks * 8), 256, 0, st>>>(qkv, out);
   } else {
@@ -251,11 +229,5 @@ int launch_attention_f32(const float* qkv, float* out, int64_t n_chunks, int L, 
   return 0;
 }
 
-int launch_attention_enc_f16(const __half* qkv, __half* out, int64_t n_chunks, cudaStream_t st) {
-  if (n_chunks == 0) return 0;
-  k_attention_enc_f32<__half, __half><<<(unsigned)n_chunks, 128, 0, st>>>(qkv, out);
-  S2S_LAUNCH_CHECK();
-  return 0;
-}
 
 }  // namespace s2s

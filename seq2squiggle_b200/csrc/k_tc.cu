@@ -69,34 +69,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// LayerNorm over the 64 values a thread holds for its row (biased variance, eps 1e-5), then write the
-// fp32 row (next residual) and the fp16 row (next GEMM operand).
-template <bool kStore32, bool kStore16>
-__device__ __forceinline__ void layernorm_store(float (&v)[64], const float* s_g, const float* s_b,
-                                                float* __restrict__ out32, __half* __restrict__ out16) {
-  float mean = 0.f;
-#pragma unroll
-  for (int i = 0; i < 64; ++i) mean += v[i];
-  mean *= (1.f / 64.f);
-  float var = 0.f;
-#pragma unroll
-  for (int i = 0; i < 64; ++i) { float d = v[i] - mean; var = fmaf(d, d, var); }
-  const float rstd = 1.0f / sqrtf(var * (1.f / 64.f) + 1e-5f);
-#pragma unroll
-  for (int i = 0; i < 64; ++i) v[i] = (v[i] - mean) * rstd * s_g[i] + s_b[i];
-  if (kStore32) {
-#pragma unroll
-    for (int i = 0; i < 64; i += 4)
-      *reinterpret_cast<float4*>(out32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-  }
-  if (kStore16) {
-#pragma unroll
-    for (int i = 0; i < 64; i += 8)
-      *reinterpret_cast<uint4*>(out16 + i) = make_uint4(pack_half2(v[i], v[i + 1]), pack_half2(v[i + 2], v[i + 3]),
-                                                         pack_half2(v[i + 4], v[i + 5]), pack_half2(v[i + 6], v[i + 7]));
-  }
-}
-
 // =================================================================================================
 // ATT: fused QKV projection + attention for one (chunk, group of 4 heads).  128 threads = 128 rows of a tile,
 // 2 CTAs / SM (TMEM 256 columns and ~109 KB of shared memory each) so one CTA's MMA round trips and row-max
@@ -412,19 +384,6 @@ __device__ __forceinline__ void out_head_epilogue(const float (&y)[64], const Ff
   }
 }
 
-#if defined(S2S_PHASE_TIMING) && S2S_PHASE_TIMING == 2
-// FFN phase timing: thread 0 (issues the MMAs) -> g_phase[0..7], thread 32 (pure epilogue thread) -> g_phase[8..15]
-#define PHF_DECL const int phf_base = threadIdx.x == 0 ? 0 : 8; const bool phf_on = threadIdx.x == 0 || threadIdx.x == 32; \
-  long long phf_t = clock64(); long long phf_acc[8]; _Pragma("unroll") for (int i_ = 0; i_ < 8; ++i_) phf_acc[i_] = 0;
-#define PHF(i) do { if (phf_on) { long long n_ = clock64(); phf_acc[i] += n_ - phf_t; phf_t = n_; } } while (0)
-#define PHF_FLUSH do { if (phf_on) { _Pragma("unroll") for (int i_ = 0; i_ < 8; ++i_) atomicAdd(&g_phase[phf_base + i_], (unsigned long long)phf_acc[i_]); } } while (0)
-#else
-#define PHF_DECL
-#define PHF(i) do {} while (0)
-#define PHF_FLUSH do {} while (0)
-#endif
-
-
 // Adaptive fallback gate, launched in front of k_tc_attn3.  When the previous sub-batch of this layer sent most of its
 // units to the exact kernel (hint set by k_tc_attn), running the single-reference kernel first only wastes its time
 // (measured with W_q, W_k scaled x4: 1.21 M chunks/s with both kernels, 1.95 M with the exact kernel alone): every
@@ -441,346 +400,10 @@ __global__ void k_attn_gate(const int* __restrict__ hint, int probe, int n_units
 }
 #include "k_tc_attn3.cuh"
 
-// =================================================================================================
-// FFN: X' = LN2(relu(Y W1^T + b1) W2^T + b2 + Y) with Y = LN1(O Wfc^T + b + X), one kernel, 128 rows per
-// tile, 2 CTAs / SM.  TMEM (256 columns): fc accumulator [0,64) ; then D1 [0,256) -> H fp16 packed over
-// [0,128) -> D2 [128,192).  Y (fp32) stays in registers as the second residual; its fp16 copy is written
-// (swizzled) over the consumed O tile in shared memory and is the A operand of W1.
-// =================================================================================================
-// kRes32: the residual stream is fp32 in HBM (x32 read + written, x16 written) — the encoder, whose fp32 output feeds the
-//         length regulator.  Otherwise (decoder) the residual stream is the fp16 tensor x16 itself: 384 B/row of
-//         HBM traffic instead of 768.  LayerNorm, both residual adds and the accumulators stay fp32 in registers/TMEM.
-// kOutHead: last decoder block: p = ReLU(out_linear(LN2 output)) (modules.py:140-141) from the fp32 registers, one
-//         float per row; the block output itself is not written at all.
-// Since round 2 only the encoder (<true, false>) is launched through this kernel: the decoder blocks run k_tc_fc_ffn4
-// (k_tc_ffn4.cuh, four tiles in flight per SM), which shares out_head_epilogue() and the parameter block with it.
-template <bool kRes32, bool kOutHead>
-__global__ void __launch_bounds__(128, 2) k_tc_fc_ffn(const __grid_constant__ CUtensorMap tmA,
-                                                      const __grid_constant__ CUtensorMap tmWfc,
-                                                      const __grid_constant__ CUtensorMap tmW1,
-                                                      const __grid_constant__ CUtensorMap tmW2,
-                                                      const __grid_constant__ CUtensorMap tmXout,
-                                                      const __grid_constant__ FfnParams P, float* __restrict__ x32,
-                                                      __half* __restrict__ x16, const __grid_constant__ OutEpi E,
-                                                      int n_tiles, int* status) {
-  // The per-column vectors (three biases, two LayerNorm affine pairs, out_linear) arrive as a __grid_constant__ kernel
-  // parameter: every use below has a compile-time index, so they are constant-bank operands of the FADD / FFMA itself
-  // (c[0x0][imm]) instead of ~180 LDS.128 per row from a shared-memory copy whose latency the two warps per scheduler
-  // could not hide (short-scoreboard stalls were 1.1 per issued instruction, profiles/r01_ffn_ncu.txt).
-  // Decoder block with a block output (not the last one): the new fp16 rows leave through shared memory and ONE TMA
-  // store per tile.  A thread's row is 128 contiguous bytes, so direct stores are eight 16-byte pieces at a 128-byte lane
-  // stride: 1,024 separate line transactions per tile, measured at ~1.5 k clk per tile (the out-head variant, which
-  // stores nothing, is 11 % faster).  The staging buffer is the tile's own A buffer, free once W1 has consumed Y.
-  constexpr bool kTmaStore = !kRes32 && !kOutHead;
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, bar_a[2], bar_m0, bar_m1, bar_m2;
-  __shared__ uint32_t s_tmem;
-  __shared__ int s_abort, s_go;
-  uint8_t* smem = align1024(smem_raw);
-  uint8_t* sW1 = smem;                       // [256 x 128 B]
-  uint8_t* sW2 = smem + 2 * kSlab;           // 4 K-slabs x [64 x 128 B]
-  uint8_t* sWfc = smem + 4 * kSlab;          // [64 x 128 B]
-  uint8_t* sA = smem + 4 * kSlab + 8192;     // 2 x [128 x 128 B]: O tile, overwritten by the fp16 Y tile
-  const int tid = threadIdx.x, warp = tid >> 5;
-  if (tid == 0) s_go = (*status == 0);
-  __syncthreads();
-  if (!s_go) return;
-  if (warp == 0) tmem_alloc<256>(&s_tmem);
-  if (tid == 0) {
-    mbar_init(&bar_w, 1); mbar_init(&bar_a[0], 1); mbar_init(&bar_a[1], 1);
-    mbar_init(&bar_m0, 1); mbar_init(&bar_m1, 1); mbar_init(&bar_m2, 1);
-    fence_mbar_init();
-    s_abort = 0;
-    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmWfc); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem = s_tmem;
-  const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
-  int tile = blockIdx.x;
-  if (tid == 0) {
-    mbar_arrive_expect_tx(&bar_w, 4 * kSlab + 8192);
-    tma_load_2d(sW1, &tmW1, &bar_w, 0, 0);
-#pragma unroll
-    for (int s = 0; s < 4; ++s) tma_load_2d(sW2 + s * 8192, &tmW2, &bar_w, s * 64, 0);
-    tma_load_2d(sWfc, &tmWfc, &bar_w, 0, 0);
-    if (tile < n_tiles) {
-      mbar_arrive_expect_tx(&bar_a[0], kSlab);
-      tma_load_2d(sA, &tmA, &bar_a[0], 0, tile * 128);
-    }
-  }
-  uint4 xr[8];  // decoder: fp16 residual row of the current tile, loaded one tile ahead
-  if (!kRes32 && tile < n_tiles) {
-    const uint4* rp = reinterpret_cast<const uint4*>(x16 + ((int64_t)tile * 128 + tid) * 64);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) xr[i] = rp[i];
-  }
-  wait_bar(&bar_w, 0, status, &s_abort, kErrFfnLoad);
-  const uint32_t idesc64 = umma_idesc(128, 64, kFmtF16), idesc256 = umma_idesc(128, 256, kFmtF16);
-  PHF_DECL
-  for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
-    const uint32_t ph = it & 1;
-    uint8_t* sAb = sA + buf * kSlab;
-    const int next = tile + gridDim.x;
-    if (tid == 0 && next < n_tiles) {  // the other buffer's last reader (W1 MMA of the previous tile) has completed
-      if (kTmaStore && it > 0) tma_store_wait_read();  // ... and so has the TMA store of the previous tile's output
-      mbar_arrive_expect_tx(&bar_a[buf ^ 1], kSlab);
-      tma_load_2d(sA + (buf ^ 1) * kSlab, &tmA, &bar_a[buf ^ 1], 0, next * 128);
-    }
-    wait_bar(&bar_a[buf], (it >> 1) & 1, status, &s_abort, kErrFfnLoad);
-    tcgen05_fence_after();
-    PHF(0);  // wait for the O tile (TMA)
-    if (tid == 0) {  // attention output projection
-      const uint32_t a0 = smem_u32(sAb), b0 = smem_u32(sWfc);
-#pragma unroll
-      for (int s = 0; s < 4; ++s)
-        umma_f16_ss(tmem, umma_desc_k_sw128(a0 + s * 32), umma_desc_k_sw128(b0 + s * 32), idesc64, s > 0);
-      umma_commit(&bar_m0);
-    }
-    const int64_t row = (int64_t)tile * 128 + tid;
-    float y[64];
-    if (kRes32) {  // first residual (the block input) while the MMA runs
-      const float4* rp = reinterpret_cast<const float4*>(x32 + row * 64);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float4 x = rp[i];
-        y[4 * i] = x.x + P.bfc[4 * i]; y[4 * i + 1] = x.y + P.bfc[4 * i + 1];
-        y[4 * i + 2] = x.z + P.bfc[4 * i + 2]; y[4 * i + 3] = x.w + P.bfc[4 * i + 3];
-      }
-    } else {
-      // the row was fetched one tile ahead (xr): a thread's 128-byte row is eight scattered 16-byte loads whose DRAM
-      // latency (~1.5k clk) would otherwise sit on the critical path in front of LayerNorm 1
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint4 x = xr[i];
-        const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[j]));
-          y[8 * i + 2 * j] = f.x + P.bfc[8 * i + 2 * j];
-          y[8 * i + 2 * j + 1] = f.y + P.bfc[8 * i + 2 * j + 1];
-        }
-      }
-      if (next < n_tiles) {  // tile `next` is only ever touched by this CTA: its rows are still the block input
-        const uint4* rp = reinterpret_cast<const uint4*>(x16 + ((int64_t)next * 128 + tid) * 64);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) xr[i] = rp[i];
-      }
-    }
-    PHF(1);  // fc MMA issue (thread 0) + residual -> registers
-    wait_bar(&bar_m0, ph, status, &s_abort, kErrFcMma);
-    tcgen05_fence_after();
-    PHF(2);  // wait fc MMA
-    uint32_t r[32];
-#pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-      tmem_ld_32x32(lane_addr + c0, r);
-      tmem_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) y[c0 + i] += __uint_as_float(r[i]);
-    }
-    {  // LayerNorm 1 (slf_attn.layer_norm); Y stays in registers, fp16 copy -> swizzled A tile over the O tile
-      float mean = 0.f;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) mean += y[i];
-      mean *= (1.f / 64.f);
-      float var = 0.f;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) { float d = y[i] - mean; var = fmaf(d, d, var); }
-      const float rstd = 1.0f / sqrtf(var * (1.f / 64.f) + 1e-5f);
-#pragma unroll
-      for (int i = 0; i < 64; ++i) y[i] = (y[i] - mean) * rstd * P.g1[i] + P.be1[i];
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(sAb + sw128_offset(tid, c)) =
-            make_uint4(pack_half2(y[8 * c], y[8 * c + 1]), pack_half2(y[8 * c + 2], y[8 * c + 3]),
-                       pack_half2(y[8 * c + 4], y[8 * c + 5]), pack_half2(y[8 * c + 6], y[8 * c + 7]));
-    }
-    fence_proxy_async_smem();
-    tcgen05_fence_before();
-    PHF(3);  // epilogue 1: accumulate, LayerNorm 1, fp16 Y -> shared
-    __syncthreads();
-    if (tid == 0) {  // hidden = Y W1^T
-      tcgen05_fence_after();
-      const uint32_t a0 = smem_u32(sAb), b0 = smem_u32(sW1);
-#pragma unroll
-      for (int s = 0; s < 4; ++s)
-        umma_f16_ss(tmem, umma_desc_k_sw128(a0 + s * 32), umma_desc_k_sw128(b0 + s * 32), idesc256, s > 0);
-      umma_commit(&bar_m1);
-    }
-    wait_bar(&bar_m1, ph, status, &s_abort, kErrFfnMma1);
-    tcgen05_fence_after();
-    PHF(4);  // sync + W1 issue + wait W1 MMA
-    {  // relu(D1 + b1) -> fp16, packed over the columns already consumed (loads double-buffered)
-      uint32_t rb[32];
-      tmem_ld_32x32(lane_addr, r);
-      tmem_wait_ld();
-#pragma unroll
-      for (int c = 0; c < 8; c += 2) {
-        tmem_ld_32x32(lane_addr + (c + 1) * 32, rb);
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          pk[i] = pack_half2_relu(__uint_as_float(r[2 * i]) + P.b1[c * 32 + 2 * i],
-                                  __uint_as_float(r[2 * i + 1]) + P.b1[c * 32 + 2 * i + 1]);
-        tmem_st_32x16(lane_addr + c * 16, pk);
-        tmem_wait_ld();
-        if (c + 2 < 8) tmem_ld_32x32(lane_addr + (c + 2) * 32, r);
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          pk[i] = pack_half2_relu(__uint_as_float(rb[2 * i]) + P.b1[(c + 1) * 32 + 2 * i],
-                                  __uint_as_float(rb[2 * i + 1]) + P.b1[(c + 1) * 32 + 2 * i + 1]);
-        tmem_st_32x16(lane_addr + (c + 1) * 16, pk);
-        if (c + 2 < 8) tmem_wait_ld();
-      }
-    }
-    tmem_wait_st();
-    tcgen05_fence_before();
-    PHF(5);  // epilogue 2: ReLU + pack -> TMEM
-    __syncthreads();
-    if (tid == 0) {  // D2 = H W2^T, A operand from TMEM
-      tcgen05_fence_after();
-      const uint32_t w2 = smem_u32(sW2);
-#pragma unroll
-      for (int s = 0; s < 16; ++s)
-        umma_f16_ts(tmem + 128, tmem + 8 * s, umma_desc_k_sw128(w2 + (s >> 2) * 8192 + (s & 3) * 32), idesc64, s > 0);
-      umma_commit(&bar_m2);
-    }
-#pragma unroll
-    for (int i = 0; i < 64; ++i) y[i] += P.b2[i];
-    wait_bar(&bar_m2, ph, status, &s_abort, kErrFfnMma2);
-    tcgen05_fence_after();
-    PHF(6);  // sync + W2 issue + wait W2 MMA
-#pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-      tmem_ld_32x32(lane_addr + 128 + c0, r);
-      tmem_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) y[c0 + i] += __uint_as_float(r[i]);
-    }
-    tcgen05_fence_before();
-    if constexpr (kTmaStore) {
-      layernorm_store<false, false>(y, P.g2, P.be2, nullptr, nullptr);   // normalise in registers only
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(sAb + sw128_offset(tid, c)) =
-            make_uint4(pack_half2(y[8 * c], y[8 * c + 1]), pack_half2(y[8 * c + 2], y[8 * c + 3]),
-                       pack_half2(y[8 * c + 4], y[8 * c + 5]), pack_half2(y[8 * c + 6], y[8 * c + 7]));
-      fence_proxy_async_smem();
-    } else {
-      layernorm_store<kRes32, !kOutHead>(y, P.g2, P.be2, x32 + row * 64, x16 + row * 64);
-    }
-    if (kOutHead) out_head_epilogue(y, P, E, row);
-    __syncthreads();  // all TMEM reads are done before the next tile's MMA overwrites the accumulators
-    tcgen05_fence_after();
-    if (kTmaStore && tid == 0) {
-      tma_store_2d(&tmXout, sAb, 0, tile * 128);
-      tma_store_commit();
-    }
-    PHF(7);  // epilogue 3: accumulate, LayerNorm 2, store + closing sync
-  }
-  if (kTmaStore && tid == 0) tma_store_wait_all();
-  PHF_FLUSH;
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tmem);
-}
-
 #include "k_tc_ffn4.cuh"
-
-// =================================================================================================
-// ENC-QKV: qkv[rows,192] (fp32) = X Wqkv^T + b for the encoder rows (16 per chunk; the 16-key attention itself
-// runs on CUDA cores).  128 threads, TMEM 256 columns, 2 CTAs / SM.
-// =================================================================================================
-__global__ void __launch_bounds__(128, 2) k_tc_qkv_plain(const __grid_constant__ CUtensorMap tmX,
-                                                         const __grid_constant__ CUtensorMap tmW,
-                                                         const float* __restrict__ bias, __half* __restrict__ qkv,
-                                                         int64_t n_rows, int* status) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, bar_a[2], bar_mma;
-  __shared__ uint32_t s_tmem;
-  __shared__ int s_abort, s_go;
-  __shared__ float s_bias[192];
-  uint8_t* smem = align1024(smem_raw);
-  uint8_t* sW = smem;                 // [192 x 128 B]
-  uint8_t* sA = smem + 192 * 128;     // 2 x [128 x 128 B]
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int n_tiles = (int)((n_rows + 127) / 128);
-  if (tid == 0) s_go = (*status == 0);
-  __syncthreads();
-  if (!s_go) return;
-  if (warp == 0) tmem_alloc<256>(&s_tmem);
-  if (tid == 0) {
-    mbar_init(&bar_w, 1); mbar_init(&bar_a[0], 1); mbar_init(&bar_a[1], 1); mbar_init(&bar_mma, 1);
-    fence_mbar_init();
-    s_abort = 0;
-    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW);
-  }
-  for (int i = tid; i < 192; i += 128) s_bias[i] = bias[i];
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem = s_tmem;
-  int tile = blockIdx.x;
-  if (tid == 0) {
-    mbar_arrive_expect_tx(&bar_w, 192 * 128);
-    tma_load_2d(sW, &tmW, &bar_w, 0, 0);
-    if (tile < n_tiles) {
-      mbar_arrive_expect_tx(&bar_a[0], kSlab);
-      tma_load_2d(sA, &tmX, &bar_a[0], 0, tile * 128);   // rows past n_rows are zero-filled by TMA
-    }
-  }
-  wait_bar(&bar_w, 0, status, &s_abort, kErrQkvLoad);
-  const uint32_t idesc = umma_idesc(128, 192, kFmtF16);
-  for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
-    const int buf = it & 1;
-    const int next = tile + gridDim.x;
-    if (tid == 0 && next < n_tiles) {
-      mbar_arrive_expect_tx(&bar_a[buf ^ 1], kSlab);
-      tma_load_2d(sA + (buf ^ 1) * kSlab, &tmX, &bar_a[buf ^ 1], 0, next * 128);
-    }
-    wait_bar(&bar_a[buf], (it >> 1) & 1, status, &s_abort, kErrQkvLoad);
-    tcgen05_fence_after();
-    if (tid == 0) {
-      const uint32_t a0 = smem_u32(sA + buf * kSlab), b0 = smem_u32(sW);
-#pragma unroll
-      for (int s = 0; s < 4; ++s)
-        umma_f16_ss(tmem, umma_desc_k_sw128(a0 + s * 32), umma_desc_k_sw128(b0 + s * 32), idesc, s > 0);
-      umma_commit(&bar_mma);
-    }
-    wait_bar(&bar_mma, it & 1, status, &s_abort, kErrQkvMma);
-    tcgen05_fence_after();
-    const int64_t row = (int64_t)tile * 128 + tid;
-    const uint32_t lane_addr = tmem_addr(tmem, warp * 32, 0);
-    uint32_t r[32];
-#pragma unroll
-    for (int c0 = 0; c0 < 192; c0 += 32) {
-      tmem_ld_32x32(lane_addr + c0, r);
-      tmem_wait_ld();
-      if (row < n_rows) {
-        uint4* dst = reinterpret_cast<uint4*>(qkv + row * 192 + c0);   // fp16 q|k|v: 384 B per row instead of 768
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          dst[i] = make_uint4(pack_half2(__uint_as_float(r[8 * i]) + s_bias[c0 + 8 * i], __uint_as_float(r[8 * i + 1]) + s_bias[c0 + 8 * i + 1]),
-                              pack_half2(__uint_as_float(r[8 * i + 2]) + s_bias[c0 + 8 * i + 2], __uint_as_float(r[8 * i + 3]) + s_bias[c0 + 8 * i + 3]),
-                              pack_half2(__uint_as_float(r[8 * i + 4]) + s_bias[c0 + 8 * i + 4], __uint_as_float(r[8 * i + 5]) + s_bias[c0 + 8 * i + 5]),
-                              pack_half2(__uint_as_float(r[8 * i + 6]) + s_bias[c0 + 8 * i + 6], __uint_as_float(r[8 * i + 7]) + s_bias[c0 + 8 * i + 7]));
-      }
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-  }
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tmem);
-}
-
 #include "k_tc_enc.cuh"
 
-constexpr int kSmemQkv = 81920;                          // 57 KB used; padded so <= 2 CTAs (TMEM 2 x 256) per SM
 constexpr int kSmemAtt = 6 * kSlab + 96 * 128 + 1024;   // 109 KB -> 2 CTAs / SM
-constexpr int kSmemFfn = 6 * kSlab + 8192 + 1024;       // 105 KB -> 2 CTAs / SM
 
 }  // namespace
 
@@ -810,15 +433,14 @@ int tc_init(TcState& s, const DevWeights& w, int device) {
     set_error("cuTensorMapEncodeTiled driver entry point not found");
     return -1;
   }
-  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_qkv_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemQkv));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_enc_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemEncAttn));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_attn3, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAtt3));
   if (const char* env = getenv("S2S_ATTN_EXACT")) s.attn_exact = atoi(env) != 0;   // tests: the exact kernel on its own
   if (const char* env = getenv("S2S_ATTN_V1")) s.attn_exact = atoi(env) != 0;      // (older spelling)
-  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn4));
   S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn4));
+  S2S_CUDA_OK(cudaFuncSetAttribute(k_tc_fc_ffn4<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemFfn4));
   (void)w;
   S2S_CUDA_OK(cudaMalloc(&s.d_status, 256));
   S2S_CUDA_OK(cudaMemset(s.d_status, 0, 256));
@@ -883,9 +505,9 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, const OutEpi
     // one 512-thread CTA per SM running four tile pipelines over one copy of the weights (k_tc_ffn4.cuh)
     const int g4 = n_tiles < s.sm_count ? n_tiles : s.sm_count;
     if (l + 1 < w.cfg.decoder_layers)
-      k_tc_fc_ffn4<false><<<g4, kFfn4Threads, kSmemFfn4, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, b.x16, epi, n_tiles, s.d_status);
+      k_tc_fc_ffn4<false><<<g4, kFfn4Threads, kSmemFfn4, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, b.x16, nullptr, epi, n_tiles, s.d_status);
     else
-      k_tc_fc_ffn4<true><<<g4, kFfn4Threads, kSmemFfn4, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, b.x16, epi, n_tiles, s.d_status);
+      k_tc_fc_ffn4<true><<<g4, kFfn4Threads, kSmemFfn4, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, b.x16, nullptr, epi, n_tiles, s.d_status);
     S2S_LAUNCH_CHECK();
     prof_end(s, PROF_FFN, e0, n_chunks, st);
   }
@@ -894,7 +516,7 @@ int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, const OutEpi
 
 
 // Encoder FFT blocks (modules.py:82-87) on the tensor cores: rows = 16 per chunk.  x32/x16 in place.
-int tc_encoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, __half* x16, float* qkv32, __half* o16,
+int tc_encoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, __half* x16, __half* o16,
                int64_t n_chunks, cudaStream_t st) {
   if (n_chunks == 0) return 0;
   EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(s.encode_tiled);
@@ -922,18 +544,11 @@ int tc_encoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, 
       set_error("cuTensorMapEncodeTiled failed for a weight tensor");
       return -1;
     }
-    static const bool enc_fused = !(getenv("S2S_ENC_FUSED") && atoi(getenv("S2S_ENC_FUSED")) == 0);   // A/B switch
-    if (enc_fused) {
-      k_tc_enc_attn<<<grid2, 256, kSmemEncAttn, st>>>(tmX, tmWqkv, bl.bqkv, o16, (int64_t)rows, s.d_status);
-      S2S_LAUNCH_CHECK();
-    } else {
-      __half* qkv16 = reinterpret_cast<__half*>(qkv32);   // the fp32 scratch of the SIMT path, used as fp16 here
-      k_tc_qkv_plain<<<grid2, 128, kSmemQkv, st>>>(tmX, tmWqkv, bl.bqkv, qkv16, (int64_t)rows, s.d_status);
-      S2S_LAUNCH_CHECK();
-      if (launch_attention_enc_f16(qkv16, o16, n_chunks, st)) return -1;
-    }
-    k_tc_fc_ffn<true, false><<<grid2, 128, kSmemFfn, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, x32, x16, OutEpi{}, n_tiles,
-                                                           s.d_status);
+    // q | k | v projection + the 16-key attention (k_tc_enc.cuh), then fc + LN + FFN + LN on the fp32 residual stream
+    k_tc_enc_attn<<<grid2, 256, kSmemEncAttn, st>>>(tmX, tmWqkv, bl.bqkv, o16, (int64_t)rows, s.d_status);
+    S2S_LAUNCH_CHECK();
+    const int g4 = n_tiles < s.sm_count ? n_tiles : s.sm_count;
+    k_tc_fc_ffn4<false, true><<<g4, kFfn4Threads, kSmemFfn4, st>>>(tmO, tmWfc, tmW1, tmW2, tmX, bl.ffn, x16, x32, OutEpi{}, n_tiles, s.d_status);
     S2S_LAUNCH_CHECK();
   }
   (void)b;

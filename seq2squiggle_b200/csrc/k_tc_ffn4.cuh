@@ -43,14 +43,16 @@ __device__ __forceinline__ void ln_apply(float (&y)[64], float sum, float sq, co
   for (int i = 0; i < 64; ++i) y[i] = fmaf(fmaf(y[i], rstd, shift), g[i], b[i]);
 }
 
-template <bool kOutHead>
+// kRes32 (encoder): the residual stream is fp32 in HBM (x32 read and written, its fp16 copy x16 written by TMA as the next
+// block's GEMM operand); otherwise (decoder) the fp16 tensor x16 is the only copy of the stream.
+template <bool kOutHead, bool kRes32 = false>
 __global__ void __launch_bounds__(kFfn4Threads, 1) k_tc_fc_ffn4(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmWfc,
                                                                 const __grid_constant__ CUtensorMap tmW1,
                                                                 const __grid_constant__ CUtensorMap tmW2,
                                                                 const __grid_constant__ CUtensorMap tmXout,
                                                                 const __grid_constant__ FfnParams P,
-                                                                const __half* __restrict__ x16,
+                                                                const __half* __restrict__ x16, float* __restrict__ x32,
                                                                 const __grid_constant__ OutEpi E, int n_tiles, int* status) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[F4Bars::COUNT];
@@ -168,11 +170,16 @@ __global__ void __launch_bounds__(kFfn4Threads, 1) k_tc_fc_ffn4(const __grid_con
         tma_load_2d(sAp + (buf ^ 1) * kSlab, &tmA, &bars[F4Bars::O + 2 * p + (buf ^ 1)], 0, (tile + stride) * 128);
         // the next tile's residual rows (x16 = the tensor tmXout describes): into L2 now, so that the row loads a tile
         // later are not DRAM round trips
-        tma_prefetch_l2_2d(&tmXout, 0, (tile + stride) * 128);
+        if (!kRes32) tma_prefetch_l2_2d(&tmXout, 0, (tile + stride) * 128);
       }
-      uint32_t xr[4][8];   // first residual (the block input, fp16): four 32-byte sectors of the thread's row, in flight
-#pragma unroll         // while the fc MMA is issued and runs
-      for (int i = 0; i < 4; ++i) ldg_256(x16 + row * 64 + 16 * i, xr[i]);
+      // first residual (the block input): the 32-byte sectors of the thread's row, in flight while the fc MMA is issued
+      // and runs -- four of fp16 or eight of fp32
+      uint32_t xr[kRes32 ? 8 : 4][8];
+#pragma unroll
+      for (int i = 0; i < (kRes32 ? 8 : 4); ++i) {
+        if constexpr (kRes32) ldg_256(x32 + row * 64 + 8 * i, xr[i]);
+        else ldg_256(x16 + row * 64 + 16 * i, xr[i]);
+      }
       if (issuer) {   // attention output projection: ACC = O Wfc^T (the previous tile's D2 was read before its closing sync)
         wait_a(BAR(F4Bars::O + 2 * p + buf), ((uint32_t)it >> 1) & 1u, kErrFfnLoad);
         tcgen05_fence_after();
@@ -185,13 +192,18 @@ __global__ void __launch_bounds__(kFfn4Threads, 1) k_tc_fc_ffn4(const __grid_con
         __syncwarp();
       }
       float y[64];
+      if constexpr (kRes32) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 64; ++i) y[i] = __uint_as_float(xr[i >> 3][i & 7]);
+      } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&xr[i][j]));
-          y[16 * i + 2 * j] = f.x;
-          y[16 * i + 2 * j + 1] = f.y;
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&xr[i][j]));
+            y[16 * i + 2 * j] = f.x;
+            y[16 * i + 2 * j + 1] = f.y;
+          }
         }
       }
       wait_a(BAR(F4Bars::FC + p), ph, kErrFcMma);
@@ -288,6 +300,14 @@ __global__ void __launch_bounds__(kFfn4Threads, 1) k_tc_fc_ffn4(const __grid_con
               make_uint4(pack_half2(y[8 * c], y[8 * c + 1]), pack_half2(y[8 * c + 2], y[8 * c + 3]),
                          pack_half2(y[8 * c + 4], y[8 * c + 5]), pack_half2(y[8 * c + 6], y[8 * c + 7])));
         fence_proxy_async_smem();
+        if constexpr (kRes32) {   // the fp32 stream: eight full sectors per row
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(x32 + row * 64 + 8 * i),
+                         "f"(y[8 * i]), "f"(y[8 * i + 1]), "f"(y[8 * i + 2]), "f"(y[8 * i + 3]), "f"(y[8 * i + 4]),
+                         "f"(y[8 * i + 5]), "f"(y[8 * i + 6]), "f"(y[8 * i + 7])
+                         : "memory");
+        }
       } else {
         out_head_epilogue(y, P, E, row);
       }

@@ -252,7 +252,7 @@ int run_pipeline(s2s_engine* h, const uint8_t* bases, const int8_t* codes, const
     pe = prof_begin(h->tc, st);
     // encoder (modules.py:82-87)
     if (tc_path) {
-      if (tc_encoder(h->tc, dw, w.tcb, w.xe, w.tcb.xe16, w.qkv_e, w.tcb.oe16, bc, st)) return -1;
+      if (tc_encoder(h->tc, dw, w.tcb, w.xe, w.tcb.xe16, w.tcb.oe16, bc, st)) return -1;
     } else {
       for (int l = 0; l < h->cfg.encoder_layers; ++l)
         if (fft_block_f32(dw.enc[l], w.xe, w.ye, w.qkv_e, w.att_e, w.he, bc, S2S_L_ENC, S2S_L_ENC, st)) return -1;

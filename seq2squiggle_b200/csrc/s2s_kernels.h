@@ -79,7 +79,6 @@ int launch_linear_f32(const float* X, const float* Wt, const float* b, const flo
 // L = 16 (rows_per_chunk 16) or 250 (rows_per_chunk 256: pad rows are neither keys nor written... they are zeroed)
 int launch_attention_f32(const float* qkv, float* out, int64_t n_chunks, int L, int rows_per_chunk, cudaStream_t st);
 // encoder attention (fp32 math) on fp16 q|k|v with fp16 output: the A operand of the tensor-core fc GEMM
-int launch_attention_enc_f16(const __half* qkv, __half* out, int64_t n_chunks, cudaStream_t st);
 
 // ---- k_samplers.cu ---------------------------------------------------------------------------
 // h3 [M,192] = ReLU(first layers) already computed; this applies the 64->1 heads, Softplus, clamps,

@@ -48,7 +48,7 @@ int tc_check_status(TcState& s, cudaStream_t st);
 // writes pA = clamp(165 ReLU(out_linear(.)) + noise, 0) (and the per-chunk non-zero counts) through the fused epilogue.
 int tc_decoder(TcState& s, const DevWeights& w, const TcBuffers& b, const OutEpi& epi, int64_t n_chunks, cudaStream_t st);
 // Runs all encoder layers in place on x32/x16 ([chunks*16 rows, padded to 128]); qkv32 [rows,192], o16 [rows,64] scratch.
-int tc_encoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, __half* x16, float* qkv32, __half* o16,
+int tc_encoder(TcState& s, const DevWeights& w, const TcBuffers& b, float* x32, __half* x16, __half* o16,
                int64_t n_chunks, cudaStream_t st);
 
 }  // namespace s2s

@@ -283,9 +283,9 @@ def test_shipped_library_is_blackwell_native():
         assert found, f"no kernel named *{tag}* in the library"
         return found
 
-    for tag in ("k_tc_attn3", "k_tc_fc_ffn", "k_tc_qkv_plain"):
+    for tag in ("k_tc_attn3", "k_tc_fc_ffn4", "k_tc_enc_attn"):
         for c in kernels(tag):
             assert c["UTCHMMA"] > 0 and c["LDTM"] > 0 and c["UTMALDG"] > 0 and c["SYNCS"] > 0, (tag, dict(c))
-    assert all(c["STTM"] > 0 for c in kernels("k_tc_attn3") + kernels("k_tc_fc_ffn"))   # fp16 P / hidden written back to TMEM
-    assert any(c["UTMASTG"] > 0 for c in kernels("k_tc_fc_ffn"))
+    assert all(c["STTM"] > 0 for c in kernels("k_tc_attn3") + kernels("k_tc_fc_ffn4"))   # fp16 P / hidden written back to TMEM
+    assert any(c["UTMASTG"] > 0 for c in kernels("k_tc_fc_ffn4"))
     assert all(c["MUFU"] > 0 for c in kernels("k_tc_attn3"))
