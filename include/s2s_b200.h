@@ -145,7 +145,7 @@ int s2s_compact_reads(const float* pa_dev /*[C,250]*/, const int64_t* chunk_offs
  * summed device time, the number of launches and the chunks they covered. */
 int s2s_profile_kernel(s2s_handle h, int enable, double* ms_total, int64_t* launches, int64_t* chunks);
 /* Between s2s_profile_kernel(h, 1, ..) and s2s_profile_kernel(h, 0, ..): the same three figures for one kernel group of
- * the path: "attention" (k_attn_gate + k_tc_attn3 + exact fallback), "ffn" (k_tc_fc_ffn incl. the fused output epilogue),
+ * the path: "attention" (k_attn_gate + k_tc_attn3 + exact fallback), "ffn" (k_tc_fc_ffn4 incl. the fused output epilogue),
  * "length_regulate", "compact" (scan + k_compact), "encoder", "front_end" (tokeniser / table lookups).  Synchronises. */
 int s2s_profile_kernel_group(s2s_handle h, const char* group, double* ms_total, int64_t* launches, int64_t* chunks);
 
