@@ -40,6 +40,7 @@ ATT_QKV_FLOP_PER_CHUNK_LAYER = 2 * 256 * 64 * 192          # fused QKV projectio
 FFN_FLOP_PER_CHUNK_LAYER = 2 * 256 * 64 * (64 + 256 + 256)  # fc + W1 + W2 per decoder layer (256 rows per chunk)
 FFN_BYTES_PER_CHUNK_LAYER = 256 * 384                       # o16 read + x16 read + x16 written, 128 B per row each
 LR_BYTES_PER_CHUNK = 2048 + 64 + 64 + 32000 + 1000 + 4      # enc_out, sigma, dur in; features, sigma_ext, total out
+LR_WRITE_SHARE = (32000 + 1000 + 4) / LR_BYTES_PER_CHUNK      # 0.94: the kernel is store-dominated
 COMPACT_BYTES_PER_CHUNK_FIXED = 1000 + 4 + 8                # pA read, count read, offset written (+ 2 B per emitted sample)
 
 
@@ -374,6 +375,16 @@ def run_ours(args):
         src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
         sm_mhz = (clk or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
         att = kt["attention"]
+        # write-only HBM rate of this GPU, measured here (the driver's peak is a COPY rate; a store-dominated kernel such as
+        # the length regulator -- 94 % of its bytes are writes -- is bounded by this one): fill of a 2 GiB buffer, best of 5
+        wbuf = torch.empty(1 << 31, dtype=torch.uint8, device=dev)
+        w_ms = []
+        for _ in range(6):
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0.record(); wbuf.fill_(1); w1.record(); torch.cuda.synchronize()
+            w_ms.append(w0.elapsed_time(w1))
+        hbm_write_peak = wbuf.numel() / (min(w_ms[1:]) * 1e-3) / 1e9
+        del wbuf
         cpl, sec = att["chunks_per_launch"], att["ms_per_launch"] * 1e-3
         exp_rate = ATT_EXP_PER_CHUNK_LAYER * cpl / sec
         exp_peak = MUFU_PER_CLK_SM * 148 * sm_mhz * 1e6
@@ -409,8 +420,9 @@ def run_ours(args):
             f = kt["length_regulate"]
             ach = LR_BYTES_PER_CHUNK * f["chunks_per_launch"] / (f["ms_per_launch"] * 1e-3) / 1e9
             kernels.append({"kernel": "k_length_regulate16", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": ach / hbm_peak, "ms_per_launch": f["ms_per_launch"], "launches_timed": f["launches"],
-                            "share_of_step": f["share"]})
+                            "frac": ach / hbm_peak, "write_share_of_bytes": LR_WRITE_SHARE,
+                            "frac_of_write_only_peak": ach / hbm_write_peak, "ms_per_launch": f["ms_per_launch"],
+                            "launches_timed": f["launches"], "share_of_step": f["share"]})
         if "compact" in kt:
             f = kt["compact"]
             byt = (COMPACT_BYTES_PER_CHUNK_FIXED + 2.0 * samples / max(chunks, 1)) * f["chunks_per_launch"]
@@ -424,7 +436,9 @@ def run_ours(args):
                 kernels.append({"kernel": name, "ms_per_launch": f["ms_per_launch"], "launches_timed": f["launches"],
                                 "share_of_step": f["share"]})
         line["kernels"] = kernels
-        line["peaks"] = {"hbm_gbs": hbm_peak, "bf16_tflops_sustained": tf_peak, "source": src}
+        line["peaks"] = {"hbm_gbs": hbm_peak, "bf16_tflops_sustained": tf_peak, "source": src,
+                         "hbm_write_only_gbs": hbm_write_peak,
+                         "hbm_write_only_source": "torch fill_ of 2 GiB timed in this run (best of 5)"}
     if args.cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
