@@ -32,7 +32,8 @@ struct s2s_engine {
   float* d_f32 = nullptr;   // derived fp32 weights
   __half* d_f16 = nullptr;  // fp16 operand copies (tcgen05 path)
   DevWeights dw{};
-  int64_t batch_chunks = 32768;  // chunks per sub-batch of the tensor-core path (S2S_BATCH_CHUNKS)
+  int64_t batch_chunks = 65536;  // chunks per sub-batch of the tensor-core path (S2S_BATCH_CHUNKS): 4.6 GB of workspace;
+                                 // 32768 -> 65536 is +1.0 % (fewer kernel heads and tails), 131072 another +0.2 %
   int64_t batch_chunks_f32 = 1024;  // fp32 parity path: its fp32 scratch is 2.6 MB per chunk
   TcState tc{};
   // per-k-mer tables of the front end (S2S_KMER_TABLES=0 disables them): built by s2s_create for k <= 9
