@@ -173,29 +173,36 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
     A3PH_DECL
     for (int it = 0; it < n_it; ++it) {
       if (lds_u32(abort_a)) break;
-      uint32_t slot = 0;
       A3PH(5);
       bool ready = mbar_try_wait_a(barS, bits & 1u);
+      // 16 quarters over the ring of three slots, unrolled by three so that slot addresses are immediates
 #pragma unroll 1
-      for (int j = 0; j < 16; ++j) {
-        const uint32_t cb = slot, cpar = (bits >> slot) & 1u;
-        bits ^= 1u << slot;
-        slot = (slot == 2u) ? 0u : slot + 1u;
-        if (!ready) wait_a(barS + 8u * cb, cpar, kErrAttS);
-        A3PH(0);
-        tcgen05_fence_after();
-        uint32_t ra[32];
-        tmem_ld_32x32(lane_addr + 64 * cb, ra);
-        // probe the next quarter's barrier now; the answer is only looked at after the exponentials
-        ready = (j < 15) ? mbar_try_wait_a(barS + 8u * slot, (bits >> slot) & 1u) : false;
-        tmem_wait_ld();
-        A3PH(1);
-        exp32_store<kPoly3H2>(ra, lane_addr + 64 * cb);
-        A3PH(2);
-        tmem_wait_st();
-        tcgen05_fence_before();
-        warp_arrive_a(barP + 8u * cb);
-        A3PH(4);
+      for (int j0 = 0; j0 < 18; j0 += 3) {
+#pragma unroll
+        for (int cb = 0; cb < 3; ++cb) {
+          if (j0 + cb < 16) {
+            constexpr uint32_t kNoop = 0;
+            (void)kNoop;
+            const uint32_t cpar = (bits >> cb) & 1u;
+            bits ^= 1u << cb;
+            const int nb = cb == 2 ? 0 : cb + 1;   // next slot
+            if (!ready) wait_a(barS + 8u * cb, cpar, kErrAttS);
+            A3PH(0);
+            tcgen05_fence_after();
+            uint32_t ra[32];
+            tmem_ld_32x32(lane_addr + 64 * cb, ra);
+            // probe the next quarter's barrier now; the answer is only looked at after the exponentials
+            ready = (j0 + cb < 15) ? mbar_try_wait_a(barS + 8u * nb, (bits >> nb) & 1u) : false;
+            tmem_wait_ld();
+            A3PH(1);
+            exp32_store<kPoly3H2>(ra, lane_addr + 64 * cb);
+            A3PH(2);
+            tmem_wait_st();
+            tcgen05_fence_before();
+            warp_arrive_a(barP + 8u * cb);
+            A3PH(4);
+          }
+        }
       }
     }
     if (warp == 0) A3PH_FLUSH(0, 6);
