@@ -34,7 +34,7 @@ MUFU_PER_CLK_SM = 16                        # ex2 per clock per SM (4 per SM sub
 # k_tc_attn3, one launch of 32768 chunks, `ncu --set full` (profiles/r02_attn3_ncu.txt): dram__bytes_read.sum 1.074546 GB
 # + dram__bytes_write.sum 1.040482 GB; the algorithmic traffic is 2 x 256 rows x 128 B = 65,536 B per chunk (x16 in, o16 out)
 # (ncu's figure is just below it: the tail of the o16 stream is still in the 126 MB L2 when the counters stop)
-ATT_DRAM_BYTES_PER_CHUNK_NCU = (1.074546e9 + 1.040482e9) / 32768
+ATT_DRAM_BYTES_PER_CHUNK_NCU = (2.154755e9 + 2.155325e9) / 65536   # profiles/r02_attn3_ncu.txt (one 65536-chunk launch)
 ATT_ALGO_BYTES_PER_CHUNK = 2 * 256 * 128
 ATT_QKV_FLOP_PER_CHUNK_LAYER = 2 * 256 * 64 * 192          # fused QKV projection inside the attention kernel
 FFN_FLOP_PER_CHUNK_LAYER = 2 * 256 * 64 * (64 + 256 + 256)  # fc + W1 + W2 per decoder layer (256 rows per chunk)
