@@ -164,8 +164,7 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
     // Four warpgroups: (query tile, half of every 64-key quarter).  Both halves of a tile work on the same ring slot: half
     // h loads S columns [32 h, 32 h + 32) and writes its 16 packed P columns at [32 h, 32 h + 16) of the slot (inside its
     // own S columns, so it cannot overwrite scores the other half has not loaded yet).  Four softmax warps per scheduler
-    // cover each other's barrier / TMEM round trips; the barrier of the next quarter is probed before this quarter's
-    // exponentials so that its ~100 clk round trip is hidden too.
+    // cover each other's barrier / TMEM round trips.
     const int wg = warp >> 3, half = (warp >> 2) & 1;
     const uint32_t lane_addr = tmem_addr(0u, (warp & 3) * 32, 208 * wg + 32 * half);
     const uint32_t barS = BAR(A3Bars::S + 3 * wg), barP = BAR(A3Bars::P + 3 * wg);
@@ -174,36 +173,36 @@ __global__ void __launch_bounds__(kAttn3Threads, 1) k_tc_attn3(const __grid_cons
     for (int it = 0; it < n_it; ++it) {
       if (lds_u32(abort_a)) break;
       A3PH(5);
-      bool ready = mbar_try_wait_a(barS, bits & 1u);
-      // 16 quarters over the ring of three slots, unrolled by three so that slot addresses are immediates
-#pragma unroll 1
-      for (int j0 = 0; j0 < 18; j0 += 3) {
-#pragma unroll
-        for (int cb = 0; cb < 3; ++cb) {
-          if (j0 + cb < 16) {
-            constexpr uint32_t kNoop = 0;
-            (void)kNoop;
-            const uint32_t cpar = (bits >> cb) & 1u;
-            bits ^= 1u << cb;
-            const int nb = cb == 2 ? 0 : cb + 1;   // next slot
-            if (!ready) wait_a(barS + 8u * cb, cpar, kErrAttS);
-            A3PH(0);
-            tcgen05_fence_after();
-            uint32_t ra[32];
-            tmem_ld_32x32(lane_addr + 64 * cb, ra);
-            // probe the next quarter's barrier now; the answer is only looked at after the exponentials
-            ready = (j0 + cb < 15) ? mbar_try_wait_a(barS + 8u * nb, (bits >> nb) & 1u) : false;
-            tmem_wait_ld();
-            A3PH(1);
-            exp32_store<kPoly3H2>(ra, lane_addr + 64 * cb);
-            A3PH(2);
-            tmem_wait_st();
-            tcgen05_fence_before();
-            warp_arrive_a(barP + 8u * cb);
-            A3PH(4);
-          }
-        }
+      // 16 quarters over the ring of three slots, unrolled by three so that slot addresses and barrier offsets are
+      // immediates: five rounds of three and the last quarter (slot 0) on its own.  The four softmax warps of a scheduler are
+      // issue-bound while they are in their exponentials, so every instruction around them counts: an early probe of the next
+      // quarter's barrier (to hide its ~100 clk round trip) cost more in bookkeeping than it hid (3.451 vs 3.425 ms).
+#define A3_QUARTER(cb)                                                                                   \
+      {                                                                                                    \
+        const uint32_t cpar = (bits >> (cb)) & 1u;                                                         \
+        bits ^= 1u << (cb);                                                                                \
+        wait_a(barS + 8u * (cb), cpar, kErrAttS);                                                          \
+        A3PH(0);                                                                                           \
+        tcgen05_fence_after();                                                                             \
+        uint32_t ra[32];                                                                                   \
+        tmem_ld_32x32(lane_addr + 64 * (cb), ra);                                                          \
+        tmem_wait_ld();                                                                                    \
+        A3PH(1);                                                                                           \
+        exp32_store<kPoly3H2>(ra, lane_addr + 64 * (cb));                                                  \
+        A3PH(2);                                                                                           \
+        tmem_wait_st();                                                                                    \
+        tcgen05_fence_before();                                                                            \
+        warp_arrive_a(barP + 8u * (cb));                                                                   \
+        A3PH(4);                                                                                           \
       }
+#pragma unroll 1
+      for (int j0 = 0; j0 < 15; j0 += 3) {
+        A3_QUARTER(0)
+        A3_QUARTER(1)
+        A3_QUARTER(2)
+      }
+      A3_QUARTER(0)
+#undef A3_QUARTER
     }
     if (warp == 0) A3PH_FLUSH(0, 6);
   } else if (warp < 20) {
