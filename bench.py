@@ -31,6 +31,7 @@ FLOP_PER_CHUNK = 85_083_392
 ATT_FLOP_PER_CHUNK_LAYER = 16_000_000       # QK^T 8.0 M + PV 8.0 M per decoder layer
 ATT_EXP_PER_CHUNK_LAYER = 8 * 250 * 250     # softmax exponentials per decoder layer
 MUFU_PER_CLK_SM = 16                        # ex2 per clock per SM (4 per SM sub-partition)
+ATT_MUFU_SHARE = 10 / 16                    # k_tc_attn3: kPoly3H2 = 6 of 16 pairs by polynomial, 10 by MUFU.EX2
 # k_tc_attn3, one launch of 32768 chunks, `ncu --set full` (profiles/r02_attn3_ncu.txt): dram__bytes_read.sum 1.074546 GB
 # + dram__bytes_write.sum 1.040482 GB; the algorithmic traffic is 2 x 256 rows x 128 B = 65,536 B per chunk (x16 in, o16 out)
 # (ncu's figure is just below it: the tail of the o16 stream is still in the 126 MB L2 when the counters stop)
@@ -398,6 +399,11 @@ def run_ours(args):
                                       "ms_per_32768_chunks is the figure earlier rounds quoted)",
                             "bound": "xu", "achieved": exp_rate / 1e9, "peak": exp_peak / 1e9, "unit": "Gexp/s",
                             "frac": exp_rate / exp_peak,
+                            # 10 of every 16 exponential pairs go through MUFU.EX2 (the other 6 are the packed-fp16 polynomial on
+                            # the FMA pipe): this is how busy the MUFU unit itself is; ncu's XU-pipe figure (73 %,
+                            # profiles/r02_attn3_ncu.txt) also counts the F2FP conversions that share the pipe
+                            "mufu_share_of_exp": ATT_MUFU_SHARE, "mufu_busy_frac": ATT_MUFU_SHARE * exp_rate / exp_peak,
+                            "limiter": "issue slots (75 %) and XU pipe (73 %) together, ncu; four softmax warps per scheduler",
                             "peak_source": f"16 MUFU.EX2 / clk / SM x 148 SMs x {sm_mhz:.0f} MHz (SM clock sampled in this run)",
                             "tensor": {"achieved": tens, "peak": tf_peak, "unit": "TFLOP/s", "frac": tens / tf_peak,
                                        "peak_source": f"{src} bf16_tflops_sustained",
